@@ -1,0 +1,155 @@
+/*
+ * b200ms.h -- C-ABI of libb200ms.so: the B200 (sm_100a) implementation of Morphik's ColPali
+ * late-interaction (MaxSim) scoring path.  Plain pointers and sizes only; no C++/torch types.
+ *
+ * Drop-in boundary (reference paths relative to /root/reference):
+ *   The reference has no FFI on this path; its scorers are reached through the Python plugin
+ *   interface core/vector_store/base_vector_store.py:7-65 (BaseVectorStore).  The host mirror of that
+ *   interface lives in morphik-core_b200/store.py and calls this library through ctypes
+ *   (INTEGRATION.md shows the binding).  Each entry point below names what it replaces:
+ *
+ *   b200ms_sign_pack       <- morphik_rust binary_quantize_batch_packed  (morphik_rust/src/binary_ops.rs:147-222,
+ *                             core/utils/fast_ops.py:191-227, called from multi_vector_store.py:329-345)
+ *   b200ms_pack_pages      <- store_embeddings' per-page quantise + layout (multi_vector_store.py:681-703;
+ *                             fast_multivector_store.py:673-707 writes fp32 .npy; values are bf16-exact :674)
+ *   b200ms_set_corpus      <- the table scan source: multi_vector_embeddings rows (multi_vector_store.py:240-251)
+ *   b200ms_pack_queries    <- _binary_quantize(query) (multi_vector_store.py:731) / torch.from_numpy(q).float()
+ *                             (fast_multivector_store.py:554)
+ *   b200ms_score           <- SQL public.max_sim over every row (multi_vector_store.py:287-311,746-763) for
+ *                             B200MS_B1, and colpali_engine score_multi_vector (fast_multivector_store.py:553-555)
+ *                             for B200MS_BF16; B200MS_I8 is new (BASELINE config 3)
+ *   b200ms_topk            <- ORDER BY similarity DESC LIMIT k (multi_vector_store.py:759) / torch.topk
+ *                             (fast_multivector_store.py:556), plus the WHERE document_id IN (...) filter (:752-757)
+ *   b200ms_merge_topk      <- (new) merge of per-GPU-shard top-k lists after the NCCL all-gather
+ *   b200ms_search_host     <- MultiVectorStore.query_similar's scoring section with HOST query buffers
+ *                             (multi_vector_store.py:721-763): quantise/convert, scan, top-k, results to host
+ *   b200ms_search_device   <- same with device-resident inputs/outputs, asynchronous on the caller's stream
+ *
+ * Conventions: every function returns 0 on success or a negative B200MS_E* code; b200ms_last_error()
+ * returns a message for the last failure on that handle (or the last global failure for NULL).
+ * A handle is bound to one CUDA device and is NOT thread-safe: the caller serialises calls per handle
+ * (the Python store holds a lock and calls through asyncio.to_thread, SURVEY 8b "Threading").
+ * Device buffers passed in are caller-owned (torch tensors); the library only owns small scratch.
+ * There is no CPU fallback: without a CUDA device every compute entry point fails with B200MS_ECUDA.
+ */
+#ifndef B200MS_H_
+#define B200MS_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200MS_VERSION 100 /* 0.1.0 */
+
+/* element types */
+#define B200MS_F32 0  /* float32 source rows (ingest / query side only)            */
+#define B200MS_BF16 1 /* bfloat16 rows, 256 B per 128-d patch vector                */
+#define B200MS_I8 2   /* int8 rows, 128 B per patch vector (global symmetric scale) */
+#define B200MS_B1 3   /* sign bits, MSB-first, 16 B per patch vector                */
+#define B200MS_I32 4  /* int32 scores (I8 / B1 corpora)                             */
+
+/* error codes */
+#define B200MS_OK 0
+#define B200MS_EINVAL (-1) /* bad argument                                  */
+#define B200MS_ECUDA (-2)  /* CUDA runtime/driver failure or no device       */
+#define B200MS_ESTATE (-3) /* call order violated (e.g. score before corpus) */
+#define B200MS_ENOMEM (-4) /* scratch allocation failed                      */
+
+#define B200MS_DIM 128        /* embedding dimension of ColPali / ColQwen patch vectors */
+#define B200MS_ROW_GROUP 32   /* pages and queries are padded to multiples of 32 rows   */
+#define B200MS_MAX_K 4096     /* largest k accepted by b200ms_topk / b200ms_merge_topk  */
+
+typedef struct b200ms b200ms_t;
+
+int b200ms_version(void);
+/* Number of CUDA devices visible (0 without a driver); never fails. */
+int b200ms_device_count(void);
+int b200ms_create(int device, b200ms_t** out);
+int b200ms_destroy(b200ms_t* h);
+const char* b200ms_last_error(const b200ms_t* h);
+
+/* ---- layout helpers (host, pure arithmetic) ------------------------------------------------- */
+/* Rows a page of `len` true rows occupies in the padded corpus layout: roundup(len, 32); 0 stays 0. */
+int64_t b200ms_padded_len(int64_t len);
+/* Sum of b200ms_padded_len over page_lens[0..n_pages). */
+int64_t b200ms_padded_rows(const int32_t* page_lens, int64_t n_pages);
+/* Bytes per row for a corpus dtype (256 / 128 / 16), or 0. */
+int64_t b200ms_row_bytes(int dtype);
+/* Number of 32-row query groups for queries of the given lengths: sum ceil(len/32) (a 0-length query -> 0). */
+int64_t b200ms_query_groups(const int32_t* q_lens, int n_q);
+
+/* ---- quantise / layout (device) ------------------------------------------------------------- */
+/* x: device [rows,128] F32|BF16 -> out: device [rows,16] sign bits, bit = (float32(x) > 0), MSB first. */
+int b200ms_sign_pack(b200ms_t* h, const void* x, int src_dtype, int64_t rows, uint8_t* out, void* stream);
+
+/* Convert n_pages pages stored back to back at src (device, [sum len,128] F32|BF16) into the padded
+ * corpus layout at dst (device): page i occupies padded_len(len_i) rows, the padding rows repeat the
+ * page's last true row (max-/min-invariant, so scores are unchanged).  dst_dtype BF16: round-to-nearest-even;
+ * I8: rint(x * i8_scale) clamped to [-127,127]; B1: sign bits.  page_lens is a HOST array. */
+int b200ms_pack_pages(b200ms_t* h, const void* src, int src_dtype, const int32_t* page_lens, int64_t n_pages,
+                      void* dst, int dst_dtype, float i8_scale, void* stream);
+
+/* Attach a packed corpus (device memory, caller-owned, must stay valid until the next set_corpus/destroy).
+ * rows: [b200ms_padded_rows(page_lens), 128] of dtype BF16|I8|B1, 1024-byte aligned.  page_lens (HOST) are the
+ * TRUE lengths.  Builds the chunk->page table, the work-unit plan and the TMA descriptor. */
+int b200ms_set_corpus(b200ms_t* h, const void* rows, int dtype, const int32_t* page_lens, int64_t n_pages);
+int64_t b200ms_corpus_pages(const b200ms_t* h);
+int64_t b200ms_corpus_rows(const b200ms_t* h);
+
+/* Pack n_q queries stored back to back at q (device, [sum len,128] F32|BF16) into 32-row groups of the
+ * corpus dtype at q_packed (device, capacity >= roundup(groups,4)*32 rows; tail rows are zeroed).
+ * group_offsets_out (HOST, [n_q+1]) receives the group range of every query.  Returns group count in
+ * *n_groups_out. */
+int b200ms_pack_queries(b200ms_t* h, const void* q, int src_dtype, const int32_t* q_lens, int n_q, void* q_packed,
+                        int dst_dtype, float i8_scale, int32_t* group_offsets_out, int* n_groups_out, void* stream);
+
+/* ---- the hot path ---------------------------------------------------------------------------- */
+/* group_scores[g, p] = sum over the (<=32) tokens of group g of max over the rows of page p of <q_t, d_r>
+ *   BF16 corpus: float32 (fp32 accumulate on tcgen05);  I8: int32 exact;  B1: int32 sum_t max_r (128 - hamming).
+ * q_packed: device [roundup(n_groups,4)*32, 128] of the corpus dtype; q_lens/group_offsets (HOST) as produced by
+ * b200ms_pack_queries (B1 needs the true token counts; may be NULL for BF16/I8).
+ * group_scores: device [n_groups_padded, ld] with ld >= n_pages, n_groups_padded = roundup(n_groups,4).
+ * Pages with zero rows score 0 (COALESCE(...,0.0), multi_vector_store.py:308). */
+int b200ms_score(b200ms_t* h, const void* q_packed, int n_groups, const int32_t* q_lens, const int32_t* group_offsets,
+                 int n_q, void* group_scores, int64_t ld, void* stream);
+
+/* Per query: score[p] = scale * sum_{g in [group_offsets[q], group_offsets[q+1])} group_scores[g, p]; keep the k
+ * best pages whose bit is set in allow_mask (device, bit p&31 of word p>>5; NULL = all), ordered by score DESC
+ * then page id ASC (the reference leaves ties unspecified).  Outputs are device arrays: top_scores/top_ids
+ * [n_q, k] (unused slots: -inf / -1), top_counts [n_q].  id_base is added to every page id (global ids of a shard). */
+int b200ms_topk(b200ms_t* h, const void* group_scores, int score_dtype, int64_t n_pages, int64_t ld,
+                const int32_t* group_offsets, int n_q, const uint32_t* allow_mask, int k, float scale, int64_t id_base,
+                float* top_scores, int64_t* top_ids, int32_t* top_counts, void* stream);
+
+/* Merge candidate lists (e.g. the all-gathered per-shard top-k): cand_scores/cand_ids device [n_q, m]
+ * (entries with id < 0 are ignored) -> best k by (score DESC, id ASC).  m <= 2*B200MS_MAX_K. */
+int b200ms_merge_topk(b200ms_t* h, const float* cand_scores, const int64_t* cand_ids, int n_q, int m, int k,
+                      float* top_scores, int64_t* top_ids, int32_t* top_counts, void* stream);
+
+/* Whole query step with HOST buffers (pageable or pinned): q_host [sum q_lens,128] float32.  Copies the
+ * queries to the device, packs, scores the attached corpus, selects top-k and copies results back;
+ * synchronous.  allow_mask_host may be NULL.  score scale: BF16 1.0; B1 1/128; I8 1/(q_scale*corpus_scale). */
+int b200ms_search_host(b200ms_t* h, const float* q_host, const int32_t* q_lens, int n_q, int k,
+                       const uint32_t* allow_mask_host, float i8_q_scale, float score_scale, int64_t id_base,
+                       float* top_scores_host, int64_t* top_ids_host, int32_t* top_counts_host);
+
+/* Same with everything on the device and no synchronisation (enqueued on `stream`).  q_dev: F32|BF16. */
+int b200ms_search_device(b200ms_t* h, const void* q_dev, int src_dtype, const int32_t* q_lens, int n_q, int k,
+                         const uint32_t* allow_mask_dev, float i8_q_scale, float score_scale, int64_t id_base,
+                         float* top_scores_dev, int64_t* top_ids_dev, int32_t* top_counts_dev, void* stream);
+
+/* ---- instrumentation ------------------------------------------------------------------------- */
+/* Kernels launched by this handle since creation (bench.py's gpu_launches claim). */
+int64_t b200ms_launch_count(const b200ms_t* h);
+/* Device time (ms, CUDA events on the launching stream) of the last b200ms_score call's scoring kernels only;
+ * synchronises.  Returns a negative error code on failure. */
+float b200ms_last_score_ms(b200ms_t* h);
+/* Tuning knobs (0 keeps the default): rows per work unit, CTAs to launch. */
+int b200ms_set_tuning(b200ms_t* h, int64_t unit_rows, int max_ctas);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200MS_H_ */

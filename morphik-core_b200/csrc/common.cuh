@@ -1,0 +1,85 @@
+// common.cuh -- handle layout, error plumbing and kernel-launcher prototypes shared by the .cu files.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/b200ms.h"
+
+namespace bms {
+
+constexpr int kDim = B200MS_DIM;
+constexpr int kGroup = B200MS_ROW_GROUP;  // 32 rows: padding granule of pages and queries ("chunk")
+constexpr int kTileN = 128;               // patch rows per MMA tile (4 chunks)
+constexpr int kTileM = 128;               // query rows per MMA tile (4 groups)
+
+struct DeviceBuf {  // grow-only device scratch
+  void* p = nullptr;
+  size_t cap = 0;
+};
+
+struct Corpus {
+  const void* rows = nullptr;
+  int dtype = -1;
+  int64_t n_pages = 0;
+  int64_t n_rows = 0;    // padded rows
+  int64_t n_chunks = 0;  // n_rows / 32
+  int n_units = 0;
+  CUtensorMap tmap;      // [n_rows,128] view, box = {128 B, kTileN rows}, SWIZZLE_128B (BF16 / I8 only)
+  bool has_tmap = false;
+  bool has_empty = false;  // some page has zero rows (its score is the memset 0)
+};
+
+}  // namespace bms
+
+struct b200ms {
+  int device = 0;
+  int num_sms = 0;
+  std::string err;
+  bms::Corpus corpus;
+  // device metadata of the attached corpus
+  bms::DeviceBuf chunk_page;   // int32 [n_chunks]   page index of every 32-row chunk
+  bms::DeviceBuf unit_start;   // int32 [n_units+1]  first chunk of every work unit (page aligned)
+  bms::DeviceBuf page_start;   // int64 [n_pages+1]  first padded row of every page   (B1 kernel, pack)
+  // scratch for pack / search
+  bms::DeviceBuf meta_a, meta_b, meta_c;  // small int arrays uploaded per call
+  bms::DeviceBuf q_raw, q_packed, scores, mask, out_s, out_i, out_c;
+  void* pinned = nullptr;  // pinned host staging
+  size_t pinned_cap = 0;
+  cudaStream_t stream = nullptr;  // internal stream for *_host entry points
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool ev_valid = false;
+  int64_t launches = 0;
+  int64_t unit_rows = 4096;
+  int max_ctas = 0;
+  CUtensorMap tmap_q;  // rebuilt per score call
+};
+
+namespace bms {
+
+int set_error(b200ms_t* h, int code, const std::string& msg);
+int check_cuda(b200ms_t* h, cudaError_t e, const char* what);
+int reserve(b200ms_t* h, DeviceBuf& b, size_t bytes);
+int upload(b200ms_t* h, DeviceBuf& b, const void* src, size_t bytes, cudaStream_t s);
+int make_tmap_rows(b200ms_t* h, CUtensorMap* out, const void* base, int dtype, int64_t n_rows, int box_rows);
+
+// kernel launchers (each returns a b200ms error code and bumps h->launches)
+int launch_score_umma(b200ms_t* h, const void* q_packed, int n_groups_padded, void* group_scores, int64_t ld,
+                      cudaStream_t s);
+int launch_score_b1(b200ms_t* h, const void* q_packed, int n_groups, const int32_t* group_ntok_dev, void* group_scores,
+                    int64_t ld, cudaStream_t s);
+int launch_sign_pack(b200ms_t* h, const void* x, int src_dtype, int64_t rows, uint8_t* out, cudaStream_t s);
+int launch_chunk_page(b200ms_t* h, const int64_t* page_start_dev, int64_t n_pages, int32_t* chunk_page, cudaStream_t s);
+int launch_pack_rows(b200ms_t* h, const void* src, int src_dtype, const int64_t* src_start_dev,
+                     const int64_t* dst_start_dev, int64_t n_items, int64_t dst_rows, int pad_mode, void* dst,
+                     int dst_dtype, float i8_scale, cudaStream_t s);
+int launch_topk(b200ms_t* h, const void* group_scores, int score_dtype, int64_t n_pages, int64_t ld,
+                const int32_t* group_offsets_dev, int n_q, const uint32_t* allow_mask, int k, float scale,
+                int64_t id_base, float* top_scores, int64_t* top_ids, int32_t* top_counts, cudaStream_t s);
+int launch_merge_topk(b200ms_t* h, const float* cand_scores, const int64_t* cand_ids, int n_q, int m, int k,
+                      float* top_scores, int64_t* top_ids, int32_t* top_counts, cudaStream_t s);
+
+}  // namespace bms

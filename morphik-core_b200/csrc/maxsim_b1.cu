@@ -1,0 +1,103 @@
+// maxsim_b1.cu -- the 1-bit (sign / Hamming) MaxSim scorer.
+//
+// Replaces SQL public.max_sim(document bit[], query bit[]) evaluated by Postgres over every row of
+// multi_vector_embeddings (core/vector_store/multi_vector_store.py:287-311, scan at :746-763):
+//     score = sum_t max_r (1 - popcount(d_r XOR q_t) / 128)
+// The kernel produces the exact integer form  S[g,p] = sum_{t in group g} max_r (128 - popcount(d_r ^ q_t));
+// score = S / 128 is exact in fp32, so parity with the oracle is bit-for-bit.
+//
+// Layout: corpus rows are 16-byte MSB-first packed sign bits (core/utils/fast_ops.py:191-227), pages padded to
+// 32-row chunks by repeating the last row (min-Hamming invariant).  One warp owns one page; lane t owns query
+// token t of up to G resident 32-token groups (bits in registers).  Each 32-row chunk is fetched with ONE
+// coalesced 512-byte request (lane i loads row i as a uint4), parked in a per-warp shared-memory slab, and
+// replayed row by row as 128-bit broadcast reads; per (row, token) the work is 4 XOR + 4 POPC + 3 ADD + 1 MIN.
+// Bound: the integer POPC pipe, not HBM (16 B per patch vector) -- see DESIGN.md.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace bms {
+
+constexpr int kB1Warps = 8;
+
+template <int G>
+__global__ void __launch_bounds__(kB1Warps * 32)
+maxsim_b1_kernel(const uint4* __restrict__ rows, const int64_t* __restrict__ page_start, int64_t n_pages,
+                 const uint4* __restrict__ q_bits /*[n_groups*32]*/, const int32_t* __restrict__ group_ntok, int g_base,
+                 int n_groups, int32_t* __restrict__ group_scores, int64_t ld) {
+  __shared__ uint4 slab[kB1Warps][32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint4 q[G];
+  int ntok[G];
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    const int gg = g_base + g;
+    const bool live = gg < n_groups;
+    q[g] = live ? __ldg(q_bits + int64_t(gg) * 32 + lane) : make_uint4(0, 0, 0, 0);
+    ntok[g] = live ? __ldg(group_ntok + gg) : 0;
+  }
+  const int64_t warp_global = int64_t(blockIdx.x) * kB1Warps + warp;
+  const int64_t warp_stride = int64_t(gridDim.x) * kB1Warps;
+  for (int64_t p = warp_global; p < n_pages; p += warp_stride) {
+    const int64_t r0 = __ldg(page_start + p), r1 = __ldg(page_start + p + 1);
+    int best[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) best[g] = 129;  // min Hamming so far (129 = none)
+    for (int64_t r = r0; r < r1; r += 32) {
+      const uint4 mine = __ldg(rows + r + lane);
+      __syncwarp();
+      slab[warp][lane] = mine;
+      __syncwarp();
+#pragma unroll 8
+      for (int i = 0; i < 32; ++i) {
+        const uint4 d = slab[warp][i];
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          const int ham = __popc(d.x ^ q[g].x) + __popc(d.y ^ q[g].y) + __popc(d.z ^ q[g].z) + __popc(d.w ^ q[g].w);
+          best[g] = min(best[g], ham);
+        }
+      }
+    }
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      const int gg = g_base + g;
+      if (gg >= n_groups) break;
+      int v = (r1 > r0 && lane < ntok[g]) ? (128 - best[g]) : 0;  // empty page -> 0 (COALESCE)
+      v = warp_sum(v);
+      if (lane == 0) group_scores[int64_t(gg) * ld + p] = v;
+    }
+  }
+}
+
+int launch_score_b1(b200ms_t* h, const void* q_packed, int n_groups, const int32_t* group_ntok_dev, void* group_scores,
+                    int64_t ld, cudaStream_t s) {
+  const Corpus& c = h->corpus;
+  if (c.n_pages == 0 || n_groups == 0) return B200MS_OK;
+  int64_t want = (c.n_pages + kB1Warps - 1) / kB1Warps;
+  const int64_t cap = int64_t(h->num_sms) * 8;
+  const int grid = int(want < cap ? want : cap);
+  const uint4* rows = static_cast<const uint4*>(c.rows);
+  const int64_t* ps = static_cast<const int64_t*>(h->page_start.p);
+  const uint4* qb = static_cast<const uint4*>(q_packed);
+  int32_t* out = static_cast<int32_t*>(group_scores);
+  for (int base = 0; base < n_groups;) {
+    const int rem = n_groups - base;
+    if (rem >= 8) {
+      maxsim_b1_kernel<8><<<grid, kB1Warps * 32, 0, s>>>(rows, ps, c.n_pages, qb, group_ntok_dev, base, n_groups, out, ld);
+      base += 8;
+    } else if (rem >= 4) {
+      maxsim_b1_kernel<4><<<grid, kB1Warps * 32, 0, s>>>(rows, ps, c.n_pages, qb, group_ntok_dev, base, n_groups, out, ld);
+      base += 4;
+    } else if (rem >= 2) {
+      maxsim_b1_kernel<2><<<grid, kB1Warps * 32, 0, s>>>(rows, ps, c.n_pages, qb, group_ntok_dev, base, n_groups, out, ld);
+      base += 2;
+    } else {
+      maxsim_b1_kernel<1><<<grid, kB1Warps * 32, 0, s>>>(rows, ps, c.n_pages, qb, group_ntok_dev, base, n_groups, out, ld);
+      base += 1;
+    }
+    h->launches++;
+    if (int e = check_cuda(h, cudaGetLastError(), "launch maxsim_b1")) return e;
+  }
+  return B200MS_OK;
+}
+
+}  // namespace bms

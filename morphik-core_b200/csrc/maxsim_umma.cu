@@ -1,0 +1,344 @@
+// maxsim_umma.cu -- the float (bf16) and int8 MaxSim scorers on tcgen05 tensor cores.
+//
+// Replaces the reference's float scorer  einsum("bnd,csd->bcns").max(3).sum(2)  (colpali_engine
+// score_multi_vector, called at core/vector_store/fast_multivector_store.py:553-555) and gives the new
+// int8 variant (BASELINE config 3) the same structure.  The [B_q, C, T, P] similarity tensor is never
+// materialised: each 128x128 (query tokens x patch rows) tile lives only in TMEM.
+//
+// Data layout in HBM
+//   corpus rows   [n_rows, 128] bf16|s8, row-major, every page padded to a multiple of 32 rows ("chunks") by
+//                 repeating its last row; chunk_page[c] = page index of chunk c
+//   work units    unit_start[u] .. unit_start[u+1] = chunk range of unit u, always whole pages (so no page is
+//                 ever split across CTAs and the per-token running max never crosses a CTA boundary)
+//   queries       [n_groups*32, 128] same dtype, each query padded with zero rows to 32-row groups; an M tile is
+//                 4 groups = 128 query tokens; TMEM lane i of the accumulator = query token i of the tile
+//   scores        group_scores[g, p] (f32 | s32), g = 32-token group, p = page
+//
+// Kernel (persistent, one CTA per SM, 384 threads, warp-specialised):
+//   warp 0      TMA producer: streams 128-row patch tiles (SWIZZLE_128B boxes) through an S-stage mbarrier ring
+//   warp 1      MMA issuer: for every patch tile and every resident query tile m < NM issues the K=128
+//               contraction as 8 (bf16) / 4 (s8) tcgen05.mma 128x128xK into one of 4 TMEM accumulators
+//   warp 2      TMEM allocator
+//   warps 4-11  two epilogue warpgroups: tcgen05.ld the accumulator, per-thread max over the 32 columns of every
+//               chunk (a thread owns one query token), fold into the running max of the current page, and at a
+//               page boundary warp-shuffle-sum the 32 tokens of the group -> one score
+// Roofline: HBM-bound while resident query tokens <= ~128-256 (B_q*T), tensor-bound above.
+// Algorithmic bytes per patch vector: 256 (bf16) / 128 (s8); flops per patch vector: 256 * query tokens.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace bms {
+
+constexpr int kThreads = 384;
+constexpr int kNumAccum = 4;                     // TMEM accumulators, kTileN fp32 columns each (4*128 = 512)
+constexpr uint32_t kSubtileBytes = 128 * 128;    // 128 rows x 128 B (one swizzle-128B panel)
+constexpr uint32_t kSmemLimit = 232448;          // 227 KB opt-in maximum per CTA
+constexpr uint32_t kBarrierBytes = 1024;
+
+template <int KIND>
+struct Kind {
+  // bf16: a 256 B row is two 128 B K-panels; s8: one.  Every tcgen05.mma step consumes 32 B of K per row.
+  static constexpr int kPanels = KIND == 0 ? 2 : 1;
+  static constexpr uint32_t kTileBytes = kPanels * kSubtileBytes;
+  static constexpr int kPanelElems = KIND == 0 ? 64 : 128;  // TMA x-coordinate step per panel (elements)
+  using Acc = typename std::conditional<KIND == 0, float, int>::type;
+};
+
+__device__ __forceinline__ float acc_from_bits(uint32_t v, float) { return __uint_as_float(v); }
+__device__ __forceinline__ int acc_from_bits(uint32_t v, int) { return static_cast<int>(v); }
+__device__ __forceinline__ float acc_max(float a, float b) { return fmaxf(a, b); }
+__device__ __forceinline__ int acc_max(int a, int b) { return max(a, b); }
+__device__ __forceinline__ float acc_max3(float a, float b, float c) { return fmax3(a, b, c); }
+__device__ __forceinline__ int acc_max3(int a, int b, int c) { return imax3(a, b, c); }
+
+// max over the 32 columns a thread holds for one chunk (two independent chains for ILP)
+template <typename Acc>
+__device__ __forceinline__ Acc chunk_max(const uint32_t (&v)[32]) {
+  Acc a = acc_from_bits(v[0], Acc{});
+  Acc b = acc_from_bits(v[1], Acc{});
+#pragma unroll
+  for (int i = 2; i < 30; i += 4) {
+    a = acc_max3(a, acc_from_bits(v[i], Acc{}), acc_from_bits(v[i + 1], Acc{}));
+    b = acc_max3(b, acc_from_bits(v[i + 2], Acc{}), acc_from_bits(v[i + 3], Acc{}));
+  }
+  a = acc_max3(a, acc_from_bits(v[30], Acc{}), acc_from_bits(v[31], Acc{}));
+  return acc_max(a, b);
+}
+
+template <int KIND, int NM>
+__global__ void __launch_bounds__(kThreads, 1)
+maxsim_umma_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constant__ CUtensorMap tmap_q,
+                   const int32_t* __restrict__ chunk_page, const int32_t* __restrict__ unit_start, int n_units,
+                   int m_tile_base, int n_groups_real, typename Kind<KIND>::Acc* __restrict__ group_scores, int64_t ld,
+                   int num_stages) {
+  using K = Kind<KIND>;
+  using Acc = typename K::Acc;
+  constexpr int NWG = NM == 1 ? 1 : 2;        // epilogue warpgroups in use
+  constexpr int NMW = NM == 1 ? 1 : NM / 2;   // query tiles owned by one epilogue warpgroup
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_q = smem;                                   // NM query tiles
+  uint8_t* smem_st = smem + NM * K::kTileBytes;             // num_stages patch tiles
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_st + size_t(num_stages) * K::kTileBytes);
+  uint64_t* full = bars;                     // [num_stages] TMA -> MMA
+  uint64_t* empty = bars + 16;               // [num_stages] MMA -> TMA
+  uint64_t* tfull = bars + 32;               // [kNumAccum]  MMA -> epilogue
+  uint64_t* tempty = bars + 40;              // [kNumAccum]  epilogue -> MMA
+  uint64_t* qfull = bars + 48;               // query tiles landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 56);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_rows);
+    prefetch_tmap(&tmap_q);
+    for (int i = 0; i < num_stages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < kNumAccum; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 4);  // one arrive per epilogue warp of the owning warpgroup
+    }
+    mbar_init(qfull, 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc_512(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================================================================ TMA producer
+    if (lane == 0) {
+      const uint64_t pol_q = policy_evict_last();
+      const uint64_t pol_rows = policy_evict_first();
+      mbar_expect_tx(qfull, NM * K::kTileBytes);
+#pragma unroll
+      for (int m = 0; m < NM; ++m)
+#pragma unroll
+        for (int p = 0; p < K::kPanels; ++p)
+          tma_load_2d(&tmap_q, qfull, smem_q + m * K::kTileBytes + p * kSubtileBytes, p * K::kPanelElems,
+                      (m_tile_base + m) * kTileM, pol_q);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+        const int c0 = __ldg(unit_start + u), c1 = __ldg(unit_start + u + 1);
+        const int n_tiles = (c1 - c0 + 3) >> 2;
+        for (int t = 0; t < n_tiles; ++t) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_expect_tx(&full[stage], K::kTileBytes);
+          uint8_t* dst = smem_st + size_t(stage) * K::kTileBytes;
+          const int row0 = (c0 + 4 * t) * kGroup;
+#pragma unroll
+          for (int p = 0; p < K::kPanels; ++p)
+            tma_load_2d(&tmap_rows, &full[stage], dst + p * kSubtileBytes, p * K::kPanelElems, row0, pol_rows);
+          if (++stage == num_stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================================ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc(KIND, kTileM, kTileN);
+      mbar_wait(qfull, 0);
+      tc_fence_after();
+      const uint32_t q_addr = smem_u32(smem_q);
+      const uint32_t st_addr = smem_u32(smem_st);
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t seq = 0;
+      for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+        const int c0 = __ldg(unit_start + u), c1 = __ldg(unit_start + u + 1);
+        const int n_tiles = (c1 - c0 + 3) >> 2;
+        for (int t = 0; t < n_tiles; ++t) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t b_addr = st_addr + uint32_t(stage) * K::kTileBytes;
+#pragma unroll
+          for (int m = 0; m < NM; ++m, ++seq) {
+            const uint32_t buf = seq & (kNumAccum - 1);
+            mbar_wait(&tempty[buf], ((seq >> 2) & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + buf * kTileN;
+            const uint32_t a_addr = q_addr + uint32_t(m) * K::kTileBytes;
+#pragma unroll
+            for (int p = 0; p < K::kPanels; ++p) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {  // 4 x 32 B of K per 128 B panel
+                const uint64_t ad = umma_desc_kmajor_sw128(a_addr + p * kSubtileBytes + k * 32);
+                const uint64_t bd = umma_desc_kmajor_sw128(b_addr + p * kSubtileBytes + k * 32);
+                umma_ss<KIND>(d_tmem, ad, bd, idesc, (p | k) != 0);
+              }
+            }
+            umma_commit(&tfull[buf]);
+          }
+          umma_commit(&empty[stage]);  // stage reusable once every query tile has consumed it
+          if (++stage == num_stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ================================================================ epilogue warpgroups
+    const int wg = (warp - 4) >> 2;
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may read
+    if (wg < NWG) {
+      Acc runmax[NMW];
+      int cur_page[NMW];
+      uint32_t seq = 0;
+      const uint32_t lane_base = tmem_base + (uint32_t(quad * 32) << 16);
+
+      for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+        const int c0 = __ldg(unit_start + u), c1 = __ldg(unit_start + u + 1);
+        const int n_tiles = (c1 - c0 + 3) >> 2;
+#pragma unroll
+        for (int i = 0; i < NMW; ++i) cur_page[i] = -1;
+
+        for (int t = 0; t < n_tiles; ++t) {
+          const int cb = c0 + 4 * t;
+          int pg[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) pg[j] = (cb + j < c1) ? __ldg(chunk_page + cb + j) : -1;
+
+#pragma unroll
+          for (int m = 0; m < NM; ++m, ++seq) {
+            if (NWG == 2 && (m & 1) != wg) continue;
+            constexpr int kShift = NM == 1 ? 0 : 1;
+            const int mi = m >> kShift;
+            const uint32_t buf = seq & (kNumAccum - 1);
+            const int group = (m_tile_base + m) * 4 + quad;
+            mbar_wait(&tfull[buf], (seq >> 2) & 1);
+            tc_fence_after();
+            if (group < n_groups_real) {
+              const uint32_t taddr = lane_base + buf * kTileN;
+              uint32_t va[32], vb[32];
+              Acc cm[4];
+              tmem_ld_32x32(taddr, va);
+              tmem_ld_32x32(taddr + 32, vb);
+              tmem_ld_wait();
+              cm[0] = chunk_max<Acc>(va);
+              cm[1] = chunk_max<Acc>(vb);
+              tmem_ld_32x32(taddr + 64, va);
+              tmem_ld_32x32(taddr + 96, vb);
+              tmem_ld_wait();
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&tempty[buf]);  // accumulator drained: MMA may overwrite it
+              cm[2] = chunk_max<Acc>(va);
+              cm[3] = chunk_max<Acc>(vb);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                if (pg[j] < 0) continue;  // chunk belongs to the next unit
+                if (pg[j] != cur_page[mi]) {
+                  if (cur_page[mi] >= 0) {
+                    const Acc s = warp_sum(runmax[mi]);
+                    if (lane == 0) group_scores[int64_t(group) * ld + cur_page[mi]] = s;
+                  }
+                  cur_page[mi] = pg[j];
+                  runmax[mi] = cm[j];
+                } else {
+                  runmax[mi] = acc_max(runmax[mi], cm[j]);
+                }
+              }
+            } else {
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&tempty[buf]);
+            }
+          }
+        }
+        // unit ends on a page boundary: flush the open page of every owned query tile
+#pragma unroll
+        for (int i = 0; i < NMW; ++i) {
+          const int m = NM == 1 ? 0 : (2 * i + wg);
+          const int group = (m_tile_base + m) * 4 + quad;
+          if (group < n_groups_real && cur_page[i] >= 0) {
+            const Acc s = warp_sum(runmax[i]);
+            if (lane == 0) group_scores[int64_t(group) * ld + cur_page[i]] = s;
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_512(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- host side
+template <int KIND, int NM>
+static int launch_one(b200ms_t* h, const CUtensorMap& tq, int m_tile_base, int n_groups_real, void* scores,
+                      int64_t ld, cudaStream_t s) {
+  using K = Kind<KIND>;
+  const Corpus& c = h->corpus;
+  const uint32_t avail = kSmemLimit - 1024 /*align*/ - kBarrierBytes - NM * K::kTileBytes;
+  int stages = int(avail / K::kTileBytes);
+  if (stages > 8) stages = 8;
+  if (stages < 2) return set_error(h, B200MS_EINVAL, "maxsim_umma: not enough shared memory for 2 stages");
+  const uint32_t smem = 1024 + NM * K::kTileBytes + uint32_t(stages) * K::kTileBytes + kBarrierBytes;
+  auto kern = maxsim_umma_kernel<KIND, NM>;
+  if (int e = check_cuda(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)),
+                         "cudaFuncSetAttribute(maxsim_umma)"))
+    return e;
+  int grid = h->max_ctas > 0 ? h->max_ctas : h->num_sms;
+  if (grid > c.n_units) grid = c.n_units;
+  if (grid < 1) return B200MS_OK;
+  kern<<<grid, kThreads, smem, s>>>(c.tmap, tq, static_cast<const int32_t*>(h->chunk_page.p),
+                                   static_cast<const int32_t*>(h->unit_start.p), c.n_units, m_tile_base, n_groups_real,
+                                   static_cast<typename K::Acc*>(scores), ld, stages);
+  h->launches++;
+  return check_cuda(h, cudaGetLastError(), "launch maxsim_umma");
+}
+
+template <int KIND>
+static int launch_kind(b200ms_t* h, const CUtensorMap& tq, int n_groups_real, int n_mtiles, void* scores, int64_t ld,
+                       cudaStream_t s) {
+  constexpr int kMaxNM = KIND == 0 ? 4 : 8;
+  int base = 0;
+  while (base < n_mtiles) {
+    const int rem = n_mtiles - base;
+    int nm = 1;
+    while (nm < rem && nm < kMaxNM) nm <<= 1;  // round up: a phantom (all-zero, TMA OOB-filled) tile beats a 2nd pass
+    int e;
+    switch (nm) {
+      case 1: e = launch_one<KIND, 1>(h, tq, base, n_groups_real, scores, ld, s); break;
+      case 2: e = launch_one<KIND, 2>(h, tq, base, n_groups_real, scores, ld, s); break;
+      case 4: e = launch_one<KIND, 4>(h, tq, base, n_groups_real, scores, ld, s); break;
+      default:
+        if constexpr (KIND == 1) {
+          e = launch_one<KIND, 8>(h, tq, base, n_groups_real, scores, ld, s);
+        } else {
+          e = set_error(h, B200MS_EINVAL, "maxsim_umma: bad NM");
+        }
+    }
+    if (e) return e;
+    base += nm;
+  }
+  return B200MS_OK;
+}
+
+int launch_score_umma(b200ms_t* h, const void* q_packed, int n_groups_real, void* group_scores, int64_t ld,
+                      cudaStream_t s) {
+  const Corpus& c = h->corpus;
+  if (!c.has_tmap) return set_error(h, B200MS_ESTATE, "score: corpus has no TMA descriptor");
+  const int n_groups_padded = (n_groups_real + 3) & ~3;
+  const int n_mtiles = n_groups_padded / 4;
+  if (int e = make_tmap_rows(h, &h->tmap_q, q_packed, c.dtype, int64_t(n_groups_padded) * kGroup, kTileM)) return e;
+  if (c.dtype == B200MS_BF16) return launch_kind<0>(h, h->tmap_q, n_groups_real, n_mtiles, group_scores, ld, s);
+  return launch_kind<1>(h, h->tmap_q, n_groups_real, n_mtiles, group_scores, ld, s);
+}
+
+}  // namespace bms

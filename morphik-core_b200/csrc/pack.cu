@@ -1,0 +1,126 @@
+// pack.cu -- quantise / layout kernels on either side of the scorer.
+//
+//   sign-bit quantise + MSB-first pack : morphik_rust binary_quantize_batch_packed (morphik_rust/src/binary_ops.rs:147-222;
+//                                        authoritative Python fallback core/utils/fast_ops.py:191-227): bit = float32(x) > 0
+//   page / query padding               : new (the reference stores ragged BIT(128)[] arrays / per-page .npy files,
+//                                        multi_vector_store.py:240-251, fast_multivector_store.py:673-707)
+//
+// One warp converts one destination row (lane l owns elements 4l..4l+3); HBM traffic is one coalesced read of the
+// source row and one coalesced write of the destination row -- these kernels are copy-bound.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace bms {
+
+__device__ __forceinline__ float4 load_row4(const void* src, int src_dtype, int64_t row, int lane) {
+  if (src_dtype == B200MS_F32) {
+    return __ldg(reinterpret_cast<const float4*>(src) + row * 32 + lane);
+  }
+  const uint2 raw = __ldg(reinterpret_cast<const uint2*>(src) + row * 32 + lane);
+  float4 v;
+  v.x = __uint_as_float(raw.x << 16);
+  v.y = __uint_as_float(raw.x & 0xffff0000u);
+  v.z = __uint_as_float(raw.y << 16);
+  v.w = __uint_as_float(raw.y & 0xffff0000u);
+  return v;
+}
+
+__device__ __forceinline__ int quant_i8(float x, float scale) {
+  const float r = rintf(x * scale);  // round-half-even, like numpy.rint in the oracle
+  return int(fminf(fmaxf(r, -127.f), 127.f));
+}
+
+__device__ __forceinline__ void store_row4(void* dst, int dst_dtype, int64_t row, int lane, float4 v, float i8_scale) {
+  if (dst_dtype == B200MS_BF16) {
+    const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y);
+    const __nv_bfloat162 hi = __floats2bfloat162_rn(v.z, v.w);
+    uint2 out;
+    out.x = *reinterpret_cast<const uint32_t*>(&lo);
+    out.y = *reinterpret_cast<const uint32_t*>(&hi);
+    reinterpret_cast<uint2*>(dst)[row * 32 + lane] = out;
+  } else if (dst_dtype == B200MS_I8) {
+    const uint32_t b0 = uint32_t(quant_i8(v.x, i8_scale)) & 0xffu, b1 = uint32_t(quant_i8(v.y, i8_scale)) & 0xffu;
+    const uint32_t b2 = uint32_t(quant_i8(v.z, i8_scale)) & 0xffu, b3 = uint32_t(quant_i8(v.w, i8_scale)) & 0xffu;
+    reinterpret_cast<uint32_t*>(dst)[row * 32 + lane] = b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);
+  } else {  // B200MS_B1: element e -> byte e/8, bit 7 - e%8 (MSB first); strict > 0 (0.0, -0.0, NaN -> 0)
+    const uint32_t nib = (uint32_t(v.x > 0.f) << 3) | (uint32_t(v.y > 0.f) << 2) | (uint32_t(v.z > 0.f) << 1) |
+                         uint32_t(v.w > 0.f);
+    const uint32_t other = __shfl_down_sync(0xffffffffu, nib, 1);
+    const uint32_t byte = (nib << 4) | other;  // valid on even lanes: elements 8i..8i+7 for i = lane/2
+    const int w = lane & 3;                    // lanes 0..3 assemble the four 32-bit words of the row
+    const uint32_t word = __shfl_sync(0xffffffffu, byte, 8 * w) | (__shfl_sync(0xffffffffu, byte, 8 * w + 2) << 8) |
+                          (__shfl_sync(0xffffffffu, byte, 8 * w + 4) << 16) |
+                          (__shfl_sync(0xffffffffu, byte, 8 * w + 6) << 24);
+    if (lane < 4) reinterpret_cast<uint32_t*>(dst)[row * 4 + lane] = word;
+  }
+}
+
+// items = pages (pad_mode 0: padding rows repeat the item's last true row) or queries (pad_mode 1: zero rows).
+// src_start/dst_start: [n_items+1] row offsets in the ragged source / padded destination.  Rows of dst past
+// dst_start[n_items] (up to dst_rows) are zero-filled.
+__global__ void __launch_bounds__(256)
+pack_rows_kernel(const void* __restrict__ src, int src_dtype, const int64_t* __restrict__ src_start,
+                 const int64_t* __restrict__ dst_start, int64_t n_items, int64_t dst_rows, int pad_mode,
+                 void* __restrict__ dst, int dst_dtype, float i8_scale) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp_global = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t warp_stride = (int64_t(gridDim.x) * blockDim.x) >> 5;
+  const int64_t used_rows = n_items > 0 ? __ldg(dst_start + n_items) : 0;
+  for (int64_t r = warp_global; r < dst_rows; r += warp_stride) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r < used_rows) {
+      int64_t lo = 0, hi = n_items - 1;  // last item with dst_start[item] <= r
+      while (lo < hi) {
+        const int64_t mid = (lo + hi + 1) >> 1;
+        if (__ldg(dst_start + mid) <= r) lo = mid; else hi = mid - 1;
+      }
+      const int64_t s0 = __ldg(src_start + lo), s1 = __ldg(src_start + lo + 1);
+      const int64_t k = r - __ldg(dst_start + lo);
+      if (k < s1 - s0) {
+        v = load_row4(src, src_dtype, s0 + k, lane);
+      } else if (pad_mode == 0 && s1 > s0) {
+        v = load_row4(src, src_dtype, s1 - 1, lane);
+      }
+    }
+    store_row4(dst, dst_dtype, r, lane, v, i8_scale);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+chunk_page_kernel(const int64_t* __restrict__ page_start, int64_t n_pages, int32_t* __restrict__ chunk_page) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp_global = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t warp_stride = (int64_t(gridDim.x) * blockDim.x) >> 5;
+  for (int64_t p = warp_global; p < n_pages; p += warp_stride) {
+    const int64_t c0 = __ldg(page_start + p) / kGroup, c1 = __ldg(page_start + p + 1) / kGroup;
+    for (int64_t c = c0 + lane; c < c1; c += 32) chunk_page[c] = int32_t(p);
+  }
+}
+
+static int grid_for(b200ms_t* h, int64_t warps) {
+  int64_t blocks = (warps + 7) / 8;
+  const int64_t cap = int64_t(h->num_sms) * 16;
+  if (blocks > cap) blocks = cap;
+  return blocks < 1 ? 1 : int(blocks);
+}
+
+int launch_pack_rows(b200ms_t* h, const void* src, int src_dtype, const int64_t* src_start_dev,
+                     const int64_t* dst_start_dev, int64_t n_items, int64_t dst_rows, int pad_mode, void* dst,
+                     int dst_dtype, float i8_scale, cudaStream_t s) {
+  if (dst_rows <= 0) return B200MS_OK;
+  pack_rows_kernel<<<grid_for(h, dst_rows), 256, 0, s>>>(src, src_dtype, src_start_dev, dst_start_dev, n_items, dst_rows,
+                                                        pad_mode, dst, dst_dtype, i8_scale);
+  h->launches++;
+  return check_cuda(h, cudaGetLastError(), "launch pack_rows");
+}
+
+int launch_chunk_page(b200ms_t* h, const int64_t* page_start_dev, int64_t n_pages, int32_t* chunk_page, cudaStream_t s) {
+  if (n_pages <= 0) return B200MS_OK;
+  chunk_page_kernel<<<grid_for(h, n_pages), 256, 0, s>>>(page_start_dev, n_pages, chunk_page);
+  h->launches++;
+  return check_cuda(h, cudaGetLastError(), "launch chunk_page");
+}
+
+}  // namespace bms

@@ -1,0 +1,257 @@
+// topk.cu -- exact top-k selection over per-page scores and the merge of per-shard candidate lists.
+//
+// Replaces  ORDER BY similarity DESC LIMIT k  (core/vector_store/multi_vector_store.py:759, with the
+// WHERE document_id IN (...) filter :752-757 expressed as a page bitmask) and  torch.topk(scores, min(k, C))
+// (core/vector_store/fast_multivector_store.py:556).  The reference leaves ties unspecified; this build orders by
+// (score DESC, page id ASC), which is what the oracle's top-k does.
+//
+// topk_kernel: one 1024-thread CTA per query.  Scores are summed over the query's 32-token groups on the fly,
+// mapped to order-preserving 32-bit keys, and the k-th key is found with a 4-pass 8-bit radix select; the
+// collect pass takes every key above the threshold plus the lowest-id ties, and a shared-memory bitonic sort
+// orders the (at most 4096) winners.  Traffic: n_pages * 4 B * groups * 5 passes per query -- negligible next to the
+// corpus scan (128..256 B per patch vector, ~1000 patch vectors per page).
+#include <math_constants.h>
+
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace bms {
+
+constexpr int kTopkThreads = 1024;
+
+__device__ __forceinline__ uint32_t key_of(float s) {
+  const uint32_t u = __float_as_uint(s);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ uint32_t key_of(int s) { return uint32_t(s) ^ 0x80000000u; }
+__device__ __forceinline__ float score_of_key(uint32_t k, float) {
+  const uint32_t u = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+  return __uint_as_float(u);
+}
+__device__ __forceinline__ float score_of_key(uint32_t k, int) { return float(int(k ^ 0x80000000u)); }
+
+template <typename T>
+__device__ __forceinline__ bool page_key(const T* __restrict__ gs, int64_t ld, int g0, int g1, const uint32_t* allow,
+                                         int64_t p, uint32_t* key) {
+  if (allow && !((__ldg(allow + (p >> 5)) >> (p & 31)) & 1u)) return false;
+  T acc = T(0);
+  for (int g = g0; g < g1; ++g) acc += __ldg(gs + int64_t(g) * ld + p);
+  *key = key_of(acc);
+  return true;
+}
+
+// block-wide bitonic sort (descending) of n2 (power of two) 64-bit keys in shared memory
+__device__ void bitonic_desc_u64(uint64_t* a, int n2) {
+  for (int size = 2; size <= n2; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      __syncthreads();
+      for (int i = threadIdx.x; i < n2 / 2; i += blockDim.x) {
+        const int lo = 2 * i - (i & (stride - 1));
+        const int hi = lo + stride;
+        const bool desc = (lo & size) == 0;
+        const uint64_t x = a[lo], y = a[hi];
+        if (desc ? (x < y) : (x > y)) {
+          a[lo] = y;
+          a[hi] = x;
+        }
+      }
+    }
+  }
+  __syncthreads();
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kTopkThreads)
+topk_kernel(const T* __restrict__ gs, int64_t n_pages, int64_t ld, const int32_t* __restrict__ group_offsets,
+            const uint32_t* __restrict__ allow, int k, float scale, int64_t id_base, float* __restrict__ top_scores,
+            int64_t* __restrict__ top_ids, int32_t* __restrict__ top_counts) {
+  extern __shared__ uint64_t win[];  // [n2] winners as (key << 32) | (0xffffffff - page)
+  __shared__ uint32_t hist[256];
+  __shared__ uint32_t s_prefix, s_need, s_total, s_gt, s_eq_base;
+  __shared__ uint32_t warp_cnt[kTopkThreads / 32];
+
+  const int q = blockIdx.x;
+  const int g0 = group_offsets[q], g1 = group_offsets[q + 1];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+
+  // ---- radix select of the k-th largest key (4 x 8 bits, most significant first)
+  uint32_t prefix = 0, need = 0, total = 0;
+  for (int pass = 0; pass < 4; ++pass) {
+    const int shift = 24 - 8 * pass;
+    if (tid < 256) hist[tid] = 0;
+    __syncthreads();
+    const uint32_t hi_mask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
+    for (int64_t p = tid; p < n_pages; p += kTopkThreads) {
+      uint32_t key;
+      if (!page_key(gs, ld, g0, g1, allow, p, &key)) continue;
+      if ((key & hi_mask) == prefix) atomicAdd(&hist[(key >> shift) & 0xffu], 1u);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      if (pass == 0) {
+        uint32_t t = 0;
+        for (int b = 0; b < 256; ++b) t += hist[b];
+        s_total = t;
+        s_need = t < uint32_t(k) ? t : uint32_t(k);
+      }
+      uint32_t rem = s_need, b = 255;
+      if (rem > 0) {
+        for (;; --b) {
+          if (hist[b] >= rem) break;
+          rem -= hist[b];
+          if (b == 0) break;
+        }
+      }
+      s_prefix = prefix | (b << shift);
+      s_need = rem;  // how many keys inside bin b are still needed
+    }
+    __syncthreads();
+    prefix = s_prefix;
+    need = s_need;
+    total = s_total;
+    __syncthreads();
+  }
+  const uint32_t kk = total < uint32_t(k) ? total : uint32_t(k);
+  const uint32_t thr = prefix;    // exact k-th largest key
+  const uint32_t need_eq = need;  // ties at thr to keep (lowest page ids first)
+  int n2 = 1;
+  while (n2 < int(kk)) n2 <<= 1;
+  for (int i = tid; i < n2; i += kTopkThreads) win[i] = 0;
+  if (tid == 0) {
+    s_gt = 0;
+    s_eq_base = 0;
+  }
+  __syncthreads();
+
+  // ---- collect: keys > thr anywhere, keys == thr in ascending page order until need_eq are taken
+  if (kk > 0) {
+    const uint32_t n_gt = kk - need_eq;
+    for (int64_t base = 0; base < n_pages; base += kTopkThreads) {
+      const int64_t p = base + tid;
+      uint32_t key = 0;
+      const bool valid = p < n_pages && page_key(gs, ld, g0, g1, allow, p, &key);
+      const bool gt = valid && key > thr;
+      const bool eq = valid && key == thr;
+      if (gt) {
+        const uint32_t pos = atomicAdd(&s_gt, 1u);
+        win[pos] = (uint64_t(key) << 32) | uint64_t(0xffffffffu - uint32_t(p));
+      }
+      const uint32_t bal = __ballot_sync(0xffffffffu, eq);
+      if (lane == 0) warp_cnt[wid] = __popc(bal);
+      __syncthreads();
+      uint32_t before = s_eq_base;
+      for (int w = 0; w < wid; ++w) before += warp_cnt[w];
+      const uint32_t rank = before + __popc(bal & ((1u << lane) - 1u));
+      if (eq && rank < need_eq) win[n_gt + rank] = (uint64_t(key) << 32) | uint64_t(0xffffffffu - uint32_t(p));
+      __syncthreads();
+      if (tid == 0) {
+        uint32_t t = 0;
+        for (int w = 0; w < kTopkThreads / 32; ++w) t += warp_cnt[w];
+        s_eq_base += t;
+      }
+      __syncthreads();
+    }
+    bitonic_desc_u64(win, n2);
+  }
+  for (int i = tid; i < k; i += kTopkThreads) {
+    const bool live = uint32_t(i) < kk;
+    const uint64_t w = live ? win[i] : 0;
+    top_scores[int64_t(q) * k + i] = live ? score_of_key(uint32_t(w >> 32), T(0)) * scale : -CUDART_INF_F;
+    top_ids[int64_t(q) * k + i] = live ? int64_t(0xffffffffu - uint32_t(w)) + id_base : int64_t(-1);
+  }
+  if (tid == 0) top_counts[q] = int32_t(kk);
+}
+
+// ------------------------------------------------------------------------------------------ merge of candidate lists
+__device__ __forceinline__ bool cand_before(uint32_t ka, int64_t ia, uint32_t kb, int64_t ib) {
+  return ka > kb || (ka == kb && ia < ib);  // score DESC, id ASC; invalid entries carry key 0 / id INT64_MAX
+}
+
+__global__ void __launch_bounds__(1024)
+merge_topk_kernel(const float* __restrict__ cand_scores, const int64_t* __restrict__ cand_ids, int m, int n2, int k,
+                  float* __restrict__ top_scores, int64_t* __restrict__ top_ids, int32_t* __restrict__ top_counts) {
+  extern __shared__ uint8_t msm[];
+  int64_t* ids = reinterpret_cast<int64_t*>(msm);
+  uint32_t* keys = reinterpret_cast<uint32_t*>(ids + n2);
+  __shared__ uint32_t s_valid;
+  const int q = blockIdx.x;
+  if (threadIdx.x == 0) s_valid = 0;
+  __syncthreads();
+  uint32_t mine = 0;
+  for (int i = threadIdx.x; i < n2; i += blockDim.x) {
+    int64_t id = -1;
+    float s = 0.f;
+    if (i < m) {
+      id = cand_ids[int64_t(q) * m + i];
+      s = cand_scores[int64_t(q) * m + i];
+    }
+    const bool ok = id >= 0;
+    keys[i] = ok ? key_of(s) : 0u;
+    ids[i] = ok ? id : INT64_MAX;
+    mine += ok;
+  }
+  atomicAdd(&s_valid, mine);
+  for (int size = 2; size <= n2; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      __syncthreads();
+      for (int i = threadIdx.x; i < n2 / 2; i += blockDim.x) {
+        const int lo = 2 * i - (i & (stride - 1));
+        const int hi = lo + stride;
+        const bool fwd = (lo & size) == 0;
+        const uint32_t ka = keys[lo], kb = keys[hi];
+        const int64_t ia = ids[lo], ib = ids[hi];
+        const bool swap = fwd ? cand_before(kb, ib, ka, ia) : cand_before(ka, ia, kb, ib);
+        if (swap) {
+          keys[lo] = kb;
+          keys[hi] = ka;
+          ids[lo] = ib;
+          ids[hi] = ia;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  const uint32_t kk = s_valid < uint32_t(k) ? s_valid : uint32_t(k);
+  for (int i = threadIdx.x; i < k; i += blockDim.x) {
+    const bool live = uint32_t(i) < kk;
+    top_scores[int64_t(q) * k + i] = live ? score_of_key(keys[i], 0.f) : -CUDART_INF_F;
+    top_ids[int64_t(q) * k + i] = live ? ids[i] : int64_t(-1);
+  }
+  if (threadIdx.x == 0) top_counts[q] = int32_t(kk);
+}
+
+int launch_topk(b200ms_t* h, const void* group_scores, int score_dtype, int64_t n_pages, int64_t ld,
+                const int32_t* group_offsets_dev, int n_q, const uint32_t* allow_mask, int k, float scale,
+                int64_t id_base, float* top_scores, int64_t* top_ids, int32_t* top_counts, cudaStream_t s) {
+  if (n_q <= 0) return B200MS_OK;
+  int n2 = 1;
+  while (n2 < k) n2 <<= 1;
+  const size_t smem = size_t(n2) * sizeof(uint64_t);
+  if (score_dtype == B200MS_F32) {
+    topk_kernel<float><<<n_q, kTopkThreads, smem, s>>>(static_cast<const float*>(group_scores), n_pages, ld,
+                                                      group_offsets_dev, allow_mask, k, scale, id_base, top_scores,
+                                                      top_ids, top_counts);
+  } else {
+    topk_kernel<int><<<n_q, kTopkThreads, smem, s>>>(static_cast<const int*>(group_scores), n_pages, ld,
+                                                    group_offsets_dev, allow_mask, k, scale, id_base, top_scores,
+                                                    top_ids, top_counts);
+  }
+  h->launches++;
+  return check_cuda(h, cudaGetLastError(), "launch topk");
+}
+
+int launch_merge_topk(b200ms_t* h, const float* cand_scores, const int64_t* cand_ids, int n_q, int m, int k,
+                      float* top_scores, int64_t* top_ids, int32_t* top_counts, cudaStream_t s) {
+  if (n_q <= 0) return B200MS_OK;
+  int n2 = 2;
+  while (n2 < m) n2 <<= 1;
+  const size_t smem = size_t(n2) * (sizeof(int64_t) + sizeof(uint32_t));
+  if (int e = check_cuda(h, cudaFuncSetAttribute(merge_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)),
+                         "cudaFuncSetAttribute(merge_topk)"))
+    return e;
+  merge_topk_kernel<<<n_q, 1024, smem, s>>>(cand_scores, cand_ids, m, n2, k, top_scores, top_ids, top_counts);
+  h->launches++;
+  return check_cuda(h, cudaGetLastError(), "launch merge_topk");
+}
+
+}  // namespace bms

@@ -1,0 +1,364 @@
+"""MaxSimIndex -- a device-resident, packed multi-vector corpus plus the search calls over it.
+
+This is the piece that replaces the reference's exhaustive scorers:
+  * Postgres evaluating SQL ``max_sim`` over every ``multi_vector_embeddings`` row
+    (core/vector_store/multi_vector_store.py:287-311, 746-763)            -> dtype "binary"
+  * ``ColQwen2_5_Processor.score_multi_vector`` + ``torch.topk``
+    (core/vector_store/fast_multivector_store.py:553-557)                -> dtype "bf16"
+  * (new, BASELINE config 3) integer MaxSim over int8 patches            -> dtype "int8"
+
+PyTorch is used only to own device memory and to name the current stream; every computation goes through the
+C-ABI of libb200ms.so (``_native``).  Nothing here falls back to the CPU.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+import torch
+
+from . import _native as nat
+
+ArrayLike = Union[np.ndarray, torch.Tensor]
+
+
+def _vp(t: Optional[torch.Tensor]):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _aligned_bytes(nbytes: int, device: torch.device, align: int = 1024) -> torch.Tensor:
+    """uint8 device tensor whose data_ptr is `align`-byte aligned (set_corpus / TMA want 1024)."""
+    raw = torch.empty(max(int(nbytes), 1) + align, dtype=torch.uint8, device=device)
+    off = (-raw.data_ptr()) % align
+    return raw[off:off + max(int(nbytes), 1)]
+
+
+class MaxSimIndex:
+    """Packed corpus of pages (each a [P_i, 128] matrix of patch embeddings) on one GPU.
+
+    Layout in HBM: rows of ``row_bytes`` (bf16 256 B / int8 128 B / sign bits 16 B), every page padded to a
+    multiple of 32 rows by repeating its last row, pages back to back in insertion order.  ``page id`` = insertion index.
+    """
+
+    def __init__(self, device: int = 0, dtype: str = "bf16", i8_scale: float = 127.0, capacity_rows: int = 0):
+        if dtype not in nat.DTYPE_NAMES or nat.DTYPE_NAMES[dtype] == nat.F32:
+            raise ValueError(f"dtype must be one of bf16/int8/binary, got {dtype!r}")
+        if not torch.cuda.is_available():
+            raise nat.NativeError("MaxSimIndex needs a CUDA device (B200); there is no CPU fallback")
+        self.device = torch.device("cuda", int(device))
+        self.dtype = nat.DTYPE_NAMES[dtype]
+        self.dtype_name = dtype
+        self.row_bytes = nat.ROW_BYTES[self.dtype]
+        self.i8_scale = float(i8_scale)  # corpus AND query quantisation scale for int8 (unit-norm rows -> 127)
+        self.h = nat.Handle(int(device))
+        self._buf: Optional[torch.Tensor] = None  # aligned uint8 storage of the packed rows
+        self._cap_rows = 0
+        self._rows = 0  # padded rows in use
+        self._page_lens: List[int] = []
+        self._attached = False
+        if capacity_rows:
+            self._grow(int(capacity_rows))
+
+    # ------------------------------------------------------------------ properties
+    @property
+    def n_pages(self) -> int:
+        return len(self._page_lens)
+
+    @property
+    def n_rows_padded(self) -> int:
+        return self._rows
+
+    @property
+    def page_lens(self) -> np.ndarray:
+        return np.asarray(self._page_lens, dtype=np.int32)
+
+    @property
+    def score_scale(self) -> float:
+        """Factor that turns the kernels' raw sums into reference-scale scores."""
+        if self.dtype == nat.B1:
+            return 1.0 / 128.0  # sum_t max_r (128 - ham) / 128  == SQL max_sim
+        if self.dtype == nat.I8:
+            return 1.0 / (self.i8_scale * self.i8_scale)
+        return 1.0
+
+    def launch_count(self) -> int:
+        return int(nat.lib.b200ms_launch_count(self.h.ptr))
+
+    def last_score_ms(self) -> float:
+        ms = float(nat.lib.b200ms_last_score_ms(self.h.ptr))
+        if ms < 0:
+            self.h.check(int(ms), "b200ms_last_score_ms")
+        return ms
+
+    def set_tuning(self, unit_rows: int = 0, max_ctas: int = 0):
+        self.h.check(nat.lib.b200ms_set_tuning(self.h.ptr, int(unit_rows), int(max_ctas)), "b200ms_set_tuning")
+        self._attached = False
+
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    # ------------------------------------------------------------------ building the corpus
+    def _grow(self, need_rows: int):
+        if need_rows <= self._cap_rows:
+            return
+        new_cap = max(need_rows, int(self._cap_rows * 1.5), 4096)
+        new_buf = _aligned_bytes(new_cap * self.row_bytes, self.device)
+        if self._buf is not None and self._rows:
+            new_buf[: self._rows * self.row_bytes].copy_(self._buf[: self._rows * self.row_bytes])
+        self._buf = new_buf
+        self._cap_rows = new_cap
+        self._attached = False
+
+    def add_pages(self, pages: Sequence[ArrayLike]) -> Tuple[int, int]:
+        """Append pages ([P_i,128] float32/bfloat16; numpy on host or torch on either side).  Returns (first id, count).
+
+        Mirrors the write half of store_embeddings (multi_vector_store.py:681-703 quantise+insert;
+        fast_multivector_store.py:673-707 np.save of float32): one H2D copy of the ragged rows, one pack kernel.
+        """
+        first = self.n_pages
+        if len(pages) == 0:
+            return first, 0
+        lens = [int(p.shape[0]) for p in pages]
+        for p in pages:
+            if p.ndim != 2 or p.shape[1] != nat.DIM:
+                raise ValueError(f"page embeddings must be [P,{nat.DIM}], got {tuple(p.shape)}")
+        src, src_dtype = self._stage_rows(pages)
+        lens_c = nat.i32_array(lens)
+        add_rows = int(nat.lib.b200ms_padded_rows(lens_c, len(lens)))
+        self._grow(self._rows + add_rows)
+        dst = self._buf[self._rows * self.row_bytes:]
+        with torch.cuda.device(self.device):
+            self.h.check(
+                nat.lib.b200ms_pack_pages(self.h.ptr, _vp(src), src_dtype, lens_c, len(lens), _vp(dst), self.dtype,
+                                          ctypes.c_float(self.i8_scale), self._stream()),
+                "b200ms_pack_pages",
+            )
+        self._rows += add_rows
+        self._page_lens.extend(lens)
+        self._attached = False
+        return first, len(lens)
+
+    def _stage_rows(self, mats: Sequence[ArrayLike]) -> Tuple[torch.Tensor, int]:
+        """Concatenate ragged [n_i,128] matrices into one device tensor (float32 or bfloat16)."""
+        if all(isinstance(m, torch.Tensor) for m in mats):
+            dt = torch.bfloat16 if all(m.dtype == torch.bfloat16 for m in mats) else torch.float32
+            cat = torch.cat([m.to(device=self.device, dtype=dt) for m in mats], dim=0) if len(mats) > 1 else mats[0].to(
+                device=self.device, dtype=dt)
+            cat = cat.contiguous()
+            if cat.shape[0] == 0:
+                cat = torch.zeros((1, nat.DIM), dtype=dt, device=self.device)
+            return cat, (nat.BF16 if dt == torch.bfloat16 else nat.F32)
+        host = np.concatenate([np.asarray(m.cpu() if isinstance(m, torch.Tensor) else m, dtype=np.float32) for m in mats], axis=0)
+        if host.shape[0] == 0:
+            host = np.zeros((1, nat.DIM), dtype=np.float32)
+        return torch.from_numpy(np.ascontiguousarray(host)).to(self.device), nat.F32
+
+    def adopt_packed(self, rows: torch.Tensor, page_lens: Sequence[int]):
+        """Use an already packed device buffer (uint8 view or typed tensor, 1024-byte aligned, layout as described in the
+        class docstring) as the corpus without copying -- bench.py builds its synthetic shard this way."""
+        buf = rows.view(torch.uint8).reshape(-1)
+        if buf.data_ptr() % 1024:
+            raise ValueError("packed corpus must be 1024-byte aligned")
+        lens = [int(x) for x in page_lens]
+        lens_c = nat.i32_array(lens)
+        need = int(nat.lib.b200ms_padded_rows(lens_c, len(lens)))
+        if buf.numel() < need * self.row_bytes:
+            raise ValueError("packed buffer smaller than the page lengths imply")
+        self._buf, self._cap_rows, self._rows = buf, buf.numel() // self.row_bytes, need
+        self._page_lens = lens
+        self._attached = False
+
+    def _attach(self):
+        if self._attached:
+            return
+        lens_c = nat.i32_array(self._page_lens)
+        with torch.cuda.device(self.device):
+            torch.cuda.current_stream(self.device).synchronize()  # pack kernels ran on torch's stream
+            self.h.check(nat.lib.b200ms_set_corpus(self.h.ptr, _vp(self._buf), self.dtype, lens_c, self.n_pages),
+                         "b200ms_set_corpus")
+        self._attached = True
+
+    def compact(self, keep: Sequence[int]):
+        """Keep only the pages in `keep` (ascending old ids), renumbering them 0..len(keep)-1: device-to-device copies of
+        the surviving page runs into a fresh buffer (DELETE ... WHERE document_id, multi_vector_store.py:929-933)."""
+        keep = [int(p) for p in keep]
+        lens = self._page_lens
+        pad = [(n + 31) // 32 * 32 for n in lens]
+        starts = np.concatenate([[0], np.cumsum(pad)]).astype(np.int64)
+        new_rows = int(sum(pad[p] for p in keep))
+        new_buf = _aligned_bytes(max(new_rows, 4096) * self.row_bytes, self.device)
+        dst = 0
+        i = 0
+        while i < len(keep):  # copy maximal runs of consecutive surviving pages
+            j = i
+            while j + 1 < len(keep) and keep[j + 1] == keep[j] + 1:
+                j += 1
+            a, b = int(starts[keep[i]]) * self.row_bytes, int(starts[keep[j] + 1]) * self.row_bytes
+            new_buf[dst:dst + (b - a)].copy_(self._buf[a:b])
+            dst += b - a
+            i = j + 1
+        self._buf, self._cap_rows, self._rows = new_buf, new_buf.numel() // self.row_bytes, new_rows
+        self._page_lens = [lens[p] for p in keep]
+        self._attached = False
+
+    def packed_rows(self) -> torch.Tensor:
+        """The packed corpus as a uint8 tensor [rows_padded, row_bytes] (a view)."""
+        if self._buf is None:
+            return torch.empty((0, self.row_bytes), dtype=torch.uint8, device=self.device)
+        return self._buf[: self._rows * self.row_bytes].view(self._rows, self.row_bytes)
+
+    # ------------------------------------------------------------------ queries
+    @staticmethod
+    def _q_lens(queries: Sequence[ArrayLike]) -> List[int]:
+        for q in queries:
+            if q.ndim != 2 or q.shape[1] != nat.DIM:
+                raise ValueError(f"query embeddings must be [T,{nat.DIM}], got {tuple(q.shape)}")
+        return [int(q.shape[0]) for q in queries]
+
+    def mask_from_pages(self, allowed: np.ndarray) -> np.ndarray:
+        """bool[n_pages] -> uint32 bitmask words (bit p&31 of word p>>5), the device filter format."""
+        allowed = np.asarray(allowed, dtype=bool)
+        if allowed.shape[0] != self.n_pages:
+            raise ValueError("mask length must equal n_pages")
+        pad = (-len(allowed)) % 32
+        bits = np.concatenate([allowed, np.zeros(pad, dtype=bool)]) if pad else allowed
+        return np.packbits(bits.reshape(-1, 32), axis=1, bitorder="little").view(np.uint32).reshape(-1).copy()
+
+    def search_host(self, queries: Sequence[np.ndarray], k: int, allow_mask: Optional[np.ndarray] = None,
+                    id_base: int = 0, out: Optional[Tuple[np.ndarray, np.ndarray, np.ndarray]] = None):
+        """End-to-end query step from HOST buffers (float32 [T_i,128] each): H2D, pack, scan, top-k, D2H; synchronous.
+
+        Returns (scores float32 [n_q,k], page ids int64 [n_q,k], counts int32 [n_q]); unused slots are -inf / -1.
+        Replaces the scoring half of query_similar (multi_vector_store.py:721-763 / fast_multivector_store.py:553-557).
+        """
+        self._attach()
+        lens = self._q_lens(queries)
+        n_q = len(lens)
+        if n_q == 1:
+            q_host = np.ascontiguousarray(queries[0], dtype=np.float32)
+        else:
+            q_host = np.ascontiguousarray(np.concatenate([np.asarray(q, dtype=np.float32) for q in queries], axis=0))
+        if out is None:
+            out = (np.empty((n_q, k), np.float32), np.empty((n_q, k), np.int64), np.empty((n_q,), np.int32))
+        ts, ti, tc = out
+        mask_p = None
+        if allow_mask is not None:
+            allow_mask = np.ascontiguousarray(allow_mask, dtype=np.uint32)
+            mask_p = allow_mask.ctypes.data_as(ctypes.c_void_p)
+        self.h.check(
+            nat.lib.b200ms_search_host(self.h.ptr, q_host.ctypes.data_as(ctypes.c_void_p), nat.i32_array(lens), n_q, int(k),
+                                       mask_p, ctypes.c_float(self.i8_scale), ctypes.c_float(self.score_scale),
+                                       int(id_base), ts.ctypes.data_as(ctypes.c_void_p),
+                                       ti.ctypes.data_as(ctypes.c_void_p), tc.ctypes.data_as(ctypes.c_void_p)),
+            "b200ms_search_host",
+        )
+        return ts, ti, tc
+
+    def search_host_flat(self, q_host: Union[np.ndarray, torch.Tensor], q_lens: Sequence[int], k: int,
+                         out_scores: torch.Tensor, out_ids: torch.Tensor, out_counts: torch.Tensor,
+                         allow_mask: Optional[np.ndarray] = None, id_base: int = 0):
+        """Same as search_host for callers that keep (pinned) host buffers: q_host is [sum T,128] float32."""
+        self._attach()
+        qp = q_host.data_ptr() if isinstance(q_host, torch.Tensor) else q_host.ctypes.data
+        mask_p = None
+        if allow_mask is not None:
+            allow_mask = np.ascontiguousarray(allow_mask, dtype=np.uint32)
+            mask_p = allow_mask.ctypes.data_as(ctypes.c_void_p)
+        self.h.check(
+            nat.lib.b200ms_search_host(self.h.ptr, ctypes.c_void_p(qp), nat.i32_array(q_lens), len(q_lens), int(k), mask_p,
+                                       ctypes.c_float(self.i8_scale), ctypes.c_float(self.score_scale), int(id_base),
+                                       ctypes.c_void_p(out_scores.data_ptr()), ctypes.c_void_p(out_ids.data_ptr()),
+                                       ctypes.c_void_p(out_counts.data_ptr())),
+            "b200ms_search_host",
+        )
+
+    def search_device(self, q_dev: torch.Tensor, q_lens: Sequence[int], k: int, allow_mask_dev: Optional[torch.Tensor] = None,
+                      id_base: int = 0, out: Optional[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]] = None):
+        """Asynchronous search with device-resident queries ([sum T,128] float32|bfloat16) on torch's current stream."""
+        self._attach()
+        n_q = len(q_lens)
+        if q_dev.dtype not in (torch.float32, torch.bfloat16) or not q_dev.is_contiguous():
+            raise ValueError("q_dev must be a contiguous float32/bfloat16 tensor")
+        if out is None:
+            out = (torch.empty((n_q, k), dtype=torch.float32, device=self.device),
+                   torch.empty((n_q, k), dtype=torch.int64, device=self.device),
+                   torch.empty((n_q,), dtype=torch.int32, device=self.device))
+        ts, ti, tc = out
+        with torch.cuda.device(self.device):
+            self.h.check(
+                nat.lib.b200ms_search_device(self.h.ptr, _vp(q_dev), nat.BF16 if q_dev.dtype == torch.bfloat16 else nat.F32,
+                                             nat.i32_array(q_lens), n_q, int(k), _vp(allow_mask_dev),
+                                             ctypes.c_float(self.i8_scale), ctypes.c_float(self.score_scale), int(id_base),
+                                             _vp(ts), _vp(ti), _vp(tc), self._stream()),
+                "b200ms_search_device",
+            )
+        return ts, ti, tc
+
+    def score_groups(self, queries: Sequence[ArrayLike]):
+        """Raw kernel output for tests and diagnostics: (group_scores tensor [n_groups_padded, ld] float32|int32,
+        group_offsets int32 [n_q+1], n_pages).  Calls pack_queries + score through the C-ABI."""
+        self._attach()
+        lens = self._q_lens(queries)
+        n_q = len(lens)
+        src, src_dtype = self._stage_rows(queries)
+        lens_c = nat.i32_array(lens)
+        groups = int(nat.lib.b200ms_query_groups(lens_c, n_q))
+        gp = max((groups + 3) // 4 * 4, 4)
+        q_packed = _aligned_bytes(gp * 32 * self.row_bytes, self.device)
+        goff = (ctypes.c_int32 * (n_q + 1))()
+        ng = ctypes.c_int(0)
+        ld = (self.n_pages + 31) // 32 * 32
+        sdt = torch.float32 if self.dtype == nat.BF16 else torch.int32
+        scores = torch.zeros((gp, max(ld, 32)), dtype=sdt, device=self.device)
+        with torch.cuda.device(self.device):
+            self.h.check(
+                nat.lib.b200ms_pack_queries(self.h.ptr, _vp(src), src_dtype, lens_c, n_q, _vp(q_packed), self.dtype,
+                                            ctypes.c_float(self.i8_scale), goff, ctypes.byref(ng), self._stream()),
+                "b200ms_pack_queries",
+            )
+            self.h.check(
+                nat.lib.b200ms_score(self.h.ptr, _vp(q_packed), ng.value, lens_c, goff, n_q, _vp(scores), max(ld, 32),
+                                     self._stream()),
+                "b200ms_score",
+            )
+        return scores, np.asarray(list(goff), dtype=np.int32), self.n_pages, q_packed
+
+    def score_matrix(self, queries: Sequence[ArrayLike]) -> np.ndarray:
+        """[n_q, n_pages] scores on the reference's scale (float64 on host; the per-query sum over 32-token groups is done
+        here in float64 for diagnostics only -- the product path sums inside the top-k kernel)."""
+        scores, goff, n_pages, _ = self.score_groups(queries)
+        torch.cuda.synchronize(self.device)
+        s = scores[:, :n_pages].cpu().numpy().astype(np.float64)
+        out = np.zeros((len(goff) - 1, n_pages), dtype=np.float64)
+        for q in range(len(goff) - 1):
+            out[q] = s[goff[q]:goff[q + 1]].sum(axis=0) * self.score_scale
+        return out
+
+    def sign_pack(self, x: ArrayLike) -> torch.Tensor:
+        """[n,128] float32/bfloat16 -> uint8 [n,16] MSB-first sign bits on the device (fast_ops.binary_quantize_packed)."""
+        src, src_dtype = self._stage_rows([x])
+        n = int(x.shape[0])
+        out = torch.empty((max(n, 1), 16), dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            self.h.check(nat.lib.b200ms_sign_pack(self.h.ptr, _vp(src), src_dtype, n, _vp(out), self._stream()),
+                         "b200ms_sign_pack")
+        return out[:n]
+
+    def merge_topk(self, cand_scores: torch.Tensor, cand_ids: torch.Tensor, k: int):
+        """Merge candidate lists [n_q, m] (ids < 0 ignored) -> top-k by (score desc, id asc), on the device."""
+        n_q, m = cand_scores.shape
+        ts = torch.empty((n_q, k), dtype=torch.float32, device=self.device)
+        ti = torch.empty((n_q, k), dtype=torch.int64, device=self.device)
+        tc = torch.empty((n_q,), dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            self.h.check(
+                nat.lib.b200ms_merge_topk(self.h.ptr, _vp(cand_scores.contiguous()), _vp(cand_ids.contiguous()), n_q, m, int(k),
+                                          _vp(ts), _vp(ti), _vp(tc), self._stream()),
+                "b200ms_merge_topk",
+            )
+        return ts, ti, tc
+
+    def close(self):
+        self.h.close()
+        self._buf = None

@@ -1,0 +1,223 @@
+"""B200MultiVectorStore -- the drop-in ``BaseVectorStore`` for Morphik's ColPali (multi-vector) retrieval.
+
+Keeps the plugin contract of core/vector_store/base_vector_store.py:7-65 byte for byte (four async methods, same
+argument names/meaning, same return shapes) plus the de-facto extras callers use: ``initialize()``
+(core/app_factory.py:78-80), ``close()``, and the ``.storage`` / ``.uri`` attributes
+(core/vector_store/dual_multivector_store.py:224-232).  Semantics follow the two reference providers:
+
+  provider "postgres" (MultiVectorStore, multi_vector_store.py)   -> ``mode="binary"``: sign-bit quantise, exhaustive
+      Hamming MaxSim, score = SQL max_sim value (multiples of 1/128), ORDER BY score DESC LIMIT k.
+  provider "morphik" (FastMultiVectorStore, fast_multivector_store.py) -> ``mode="bf16"``: float MaxSim; the reference
+      reranks <=75 ANN candidates, this store scores EVERY authorised page exactly (a superset of that behaviour).
+  ``mode="int8"`` is new (BASELINE config 3).
+
+Everything heavy runs on the GPU through libb200ms (see index.py); this class only owns the id <-> (document, chunk)
+catalogue, the doc_ids -> page-mask conversion, payload bookkeeping and DocumentChunk construction.  GPU calls are
+serialised with a lock and pushed off the event loop with asyncio.to_thread (SURVEY 8b "Threading").
+"""
+from __future__ import annotations
+
+import asyncio
+import json
+import logging
+import threading
+import time
+from typing import Any, Dict, List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+
+from .catalog import PageCatalog, PageRecord
+from .models import DocumentChunk
+
+logger = logging.getLogger(__name__)
+
+try:  # inside a Morphik checkout the reference ABC is the real base class
+    from core.vector_store.base_vector_store import BaseVectorStore  # type: ignore
+except Exception:  # standalone: same abstract surface
+    from abc import ABC, abstractmethod
+
+    class BaseVectorStore(ABC):  # mirrors core/vector_store/base_vector_store.py:7-65
+        @abstractmethod
+        async def store_embeddings(self, chunks, app_id=None): ...
+
+        @abstractmethod
+        async def query_similar(self, query_embedding, k, doc_ids=None, app_id=None, skip_image_content=False): ...
+
+        @abstractmethod
+        async def get_chunks_by_id(self, chunk_identifiers, app_id=None, skip_image_content=False): ...
+
+        @abstractmethod
+        async def delete_chunks_by_document_id(self, document_id, app_id=None): ...
+
+
+def build_store_metrics(**kw) -> Dict[str, Any]:
+    """Same keys as core/vector_store/utils.py:73-103 so ingestion telemetry keeps working."""
+    base = dict(chunk_payload_upload_s=0.0, chunk_payload_objects=0, chunk_payload_bytes=0, chunk_payload_backend="memory",
+                multivector_upload_s=0.0, multivector_objects=0, multivector_bytes=0, multivector_backend="b200-hbm",
+                vector_store_write_s=0.0, vector_store_backend="b200-hbm", vector_store_rows=0, cache_write_s=0.0,
+                cache_write_objects=0)
+    base.update(kw)
+    return base
+
+
+def as_query_matrix(query_embedding) -> np.ndarray:
+    """np.ndarray | torch.Tensor | List[np.ndarray] | List[torch.Tensor] | nested lists -> float32 [T,128]
+    (accepted input forms: multi_vector_store.py:723,334-337; fast_multivector_store.py:506,515-518)."""
+    try:
+        import torch
+
+        if isinstance(query_embedding, torch.Tensor):
+            query_embedding = query_embedding.detach().float().cpu().numpy()
+        elif isinstance(query_embedding, (list, tuple)) and len(query_embedding) and isinstance(query_embedding[0], torch.Tensor):
+            query_embedding = np.stack([t.detach().float().cpu().numpy() for t in query_embedding])
+    except ImportError:  # pragma: no cover
+        pass
+    q = np.asarray(query_embedding, dtype=np.float32)
+    if q.ndim == 1:
+        q = q[None, :]
+    if q.ndim != 2 or q.shape[1] != 128:
+        raise ValueError(f"query embedding must be [T,128], got {q.shape}")
+    return np.ascontiguousarray(q)
+
+
+class B200MultiVectorStore(BaseVectorStore):
+    """Exhaustive ColPali MaxSim store on one B200 (see module docstring)."""
+
+    def __init__(self, uri: str = "b200://0", device: int = 0, mode: str = "bf16", storage: Any = None,
+                 auto_initialize: bool = True, compact_dead_fraction: float = 0.3, index: Any = None):
+        self.uri = uri
+        self.device = int(device)
+        self.mode = mode
+        self.storage = storage  # attribute kept for DualMultiVectorStore / DocumentService compatibility
+        self.compact_dead_fraction = float(compact_dead_fraction)
+        self.catalog = PageCatalog()
+        self._index = index  # injectable for host-logic tests; the product builds a MaxSimIndex in initialize()
+        self._lock = threading.Lock()
+        self._last_store_metrics: Dict[str, Any] = {}
+        self.last_query_timing: Dict[str, float] = {}
+        if auto_initialize:
+            self.initialize()
+
+    # ------------------------------------------------------------------ lifecycle
+    def initialize(self) -> bool:
+        if self._index is None:
+            from .index import MaxSimIndex  # raises when libb200ms.so or the GPU is missing: no silent fallback
+
+            self._index = MaxSimIndex(device=self.device, dtype=self.mode)
+        return True
+
+    def close(self) -> None:
+        if self._index is not None and hasattr(self._index, "close"):
+            self._index.close()
+        self._index = None
+
+    def latest_store_metrics(self) -> Dict[str, Any]:
+        return dict(self._last_store_metrics)
+
+    # ------------------------------------------------------------------ write path
+    async def store_embeddings(self, chunks: List[DocumentChunk], app_id: Optional[str] = None
+                               ) -> Tuple[bool, List[str], Dict[str, Any]]:
+        valid = []
+        for c in chunks:
+            if getattr(c, "embedding", None) is None:
+                logger.error("Missing embeddings for chunk %s-%s", c.document_id, c.chunk_number)
+                continue
+            emb = np.asarray(c.embedding.detach().float().cpu().numpy() if hasattr(c.embedding, "detach") else c.embedding,
+                             dtype=np.float32)
+            if emb.ndim == 1:
+                emb = emb[None, :]
+            if emb.ndim != 2 or emb.shape[1] != 128:
+                raise ValueError(f"chunk {c.document_id}-{c.chunk_number}: embedding must be [P,128], got {emb.shape}")
+            valid.append((c, emb))
+        if not valid:
+            self._last_store_metrics = build_store_metrics()
+            return True, [], self._last_store_metrics
+        t0 = time.perf_counter()
+        await asyncio.to_thread(self._add_pages_locked, valid, app_id)
+        dt = time.perf_counter() - t0
+        self._last_store_metrics = build_store_metrics(
+            vector_store_write_s=dt, vector_store_rows=len(valid), multivector_objects=len(valid), multivector_upload_s=dt,
+            multivector_bytes=int(sum(e.shape[0] for _, e in valid)) * self._index.row_bytes)
+        return True, [f"{c.document_id}-{c.chunk_number}" for c, _ in valid], self._last_store_metrics
+
+    def _add_pages_locked(self, valid, app_id):
+        with self._lock:
+            first, n = self._index.add_pages([e for _, e in valid])
+            for i, (c, e) in enumerate(valid):
+                pid = self.catalog.add(PageRecord(c.document_id, int(c.chunk_number), c.content, dict(c.metadata or {}),
+                                                  app_id, int(e.shape[0])))
+                assert pid == first + i, "catalogue and device corpus out of step"
+
+    # ------------------------------------------------------------------ read path
+    async def query_similar(self, query_embedding, k: int, doc_ids: Optional[List[str]] = None,
+                            app_id: Optional[str] = None, skip_image_content: bool = False) -> List[DocumentChunk]:
+        results = await self.query_similar_batch([query_embedding], k, doc_ids, app_id, skip_image_content)
+        return results[0]
+
+    async def query_similar_batch(self, query_embeddings: Sequence[Any], k: int, doc_ids: Optional[List[str]] = None,
+                                  app_id: Optional[str] = None, skip_image_content: bool = False
+                                  ) -> List[List[DocumentChunk]]:
+        """Batched form (extension): one corpus pass scores every query of the batch."""
+        t0 = time.perf_counter()
+        queries = [as_query_matrix(q) for q in query_embeddings]
+        if len(self.catalog) == 0 or k <= 0:
+            return [[] for _ in queries]
+        mask = self.catalog.allow_mask(doc_ids, app_id)
+        if mask is not None and not mask.any():
+            return [[] for _ in queries]
+        words = None if mask is None else PageCatalog.mask_words(mask)
+        kk = min(int(k), len(self.catalog), 4096)
+        t1 = time.perf_counter()
+        ts, ti, tc = await asyncio.to_thread(self._search_locked, queries, kk, words)
+        t2 = time.perf_counter()
+        out: List[List[DocumentChunk]] = []
+        for qi in range(len(queries)):
+            hits = []
+            for j in range(int(tc[qi])):
+                rec = self.catalog.records[int(ti[qi, j])]
+                hits.append(DocumentChunk(document_id=rec.document_id, chunk_number=rec.chunk_number, content=rec.content,
+                                          embedding=[], metadata=dict(rec.metadata), score=float(ts[qi, j])))
+            out.append(hits)
+        t3 = time.perf_counter()
+        self.last_query_timing = {"prepare_ms": (t1 - t0) * 1e3, "gpu_search_ms": (t2 - t1) * 1e3,
+                                  "build_chunks_ms": (t3 - t2) * 1e3, "total_ms": (t3 - t0) * 1e3}
+        logger.debug("query_similar timing %s", json.dumps(self.last_query_timing))
+        return out
+
+    def _search_locked(self, queries, k, words):
+        with self._lock:
+            return self._index.search_host(queries, k, allow_mask=words)
+
+    async def get_chunks_by_id(self, chunk_identifiers: List[Tuple[str, int]], app_id: Optional[str] = None,
+                               skip_image_content: bool = False) -> List[DocumentChunk]:
+        if not chunk_identifiers:
+            return []
+        out = []
+        for doc_id, chunk_num in dict.fromkeys((d, int(n)) for d, n in chunk_identifiers):
+            pid = self.catalog.lookup(doc_id, chunk_num)
+            if pid is None:
+                continue
+            rec = self.catalog.records[pid]
+            if app_id is not None and rec.app_id is not None and rec.app_id != app_id:
+                continue
+            out.append(DocumentChunk(document_id=rec.document_id, chunk_number=rec.chunk_number, content=rec.content,
+                                     embedding=[], metadata=dict(rec.metadata), score=0.0))
+        return out
+
+    async def delete_chunks_by_document_id(self, document_id: str, app_id: Optional[str] = None) -> bool:
+        try:
+            with self._lock:
+                self.catalog.delete_document(document_id)
+                if self.catalog.dead_fraction > self.compact_dead_fraction:
+                    self._compact_locked()
+            return True
+        except Exception as e:  # noqa: BLE001  (reference returns False on error: multi_vector_store.py:949-951)
+            logger.error("Error deleting chunks for document %s: %s", document_id, e)
+            return False
+
+    def _compact_locked(self):
+        """Drop tombstoned pages: rebuild the device corpus from the surviving packed rows (device-to-device)."""
+        keep, _ = self.catalog.compaction_plan()
+        if hasattr(self._index, "compact"):
+            self._index.compact(keep)
+        self.catalog.apply_compaction(keep)

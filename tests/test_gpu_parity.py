@@ -1,0 +1,301 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path, called through the C-ABI (ctypes), against the oracle.
+
+Bars (SURVEY 8d "Parity gates"): sign bits / Hamming / int8 bit-exact; bf16 scores within 1e-3 relative of the fp32
+oracle evaluated on the same bf16-rounded inputs (measured: ~1e-6); top-k id lists identical to the oracle's
+(score DESC, page id ASC) on inputs without near-ties, and identical as score multisets otherwise.
+"""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+if not torch.cuda.is_available():  # pragma: no cover - the gpu marker normally deselects these on CPU boxes
+    pytest.skip("CUDA device required", allow_module_level=True)
+
+from morphik_core_b200 import _native as nat  # noqa: E402
+from morphik_core_b200.index import MaxSimIndex  # noqa: E402
+from oracle import maxsim_oracle as orc  # noqa: E402
+
+BF16_RTOL = 1e-3  # north-star tolerance for bf16 storage
+
+
+def unit_rows(rng, n, d=128):
+    x = rng.standard_normal((n, d)).astype(np.float32)
+    return x / np.linalg.norm(x, axis=1, keepdims=True)
+
+
+def make_pages(rng, lens):
+    return [unit_rows(rng, n) if n > 0 else np.zeros((0, 128), np.float32) for n in lens]
+
+
+def oracle_float(queries, pages, bf16=True):
+    rows = np.concatenate(pages) if sum(len(p) for p in pages) else np.zeros((0, 128), np.float32)
+    off = orc.page_offsets([len(p) for p in pages])
+    rr = orc.bf16_round_np(rows) if bf16 else rows
+    return np.stack([orc.float_maxsim_c(orc.bf16_round_np(q) if bf16 else q, rr, off) for q in queries])
+
+
+def assert_close_rel(got, want, rtol):
+    scale = np.maximum(np.abs(want), 1e-3)
+    err = np.abs(got - want) / scale
+    assert err.max() <= rtol, f"max rel err {err.max():.3e} at {np.unravel_index(err.argmax(), err.shape)}"
+
+
+# ------------------------------------------------------------------------------------------------ quantiser (a-2)
+def test_sign_pack_matches_reference_golden(golden_dir):
+    sp = np.load(os.path.join(golden_dir, "sign_pack.npz"))
+    idx = MaxSimIndex(dtype="binary")
+    got = idx.sign_pack(sp["x"]).cpu().numpy()
+    assert np.array_equal(got, sp["packed"])  # bytes produced by the reference's own fast_ops.py
+    got_bf16 = idx.sign_pack(torch.from_numpy(sp["x"]).bfloat16().cuda()).cpu().numpy()
+    want_bf16 = orc.sign_pack_c(torch.from_numpy(sp["x"]).bfloat16().float().numpy())
+    assert np.array_equal(got_bf16, want_bf16)
+    big = np.random.default_rng(5).standard_normal((10007, 128)).astype(np.float32)
+    assert np.array_equal(idx.sign_pack(big).cpu().numpy(), orc.sign_pack_c(big))
+
+
+# ------------------------------------------------------------------------------------------------ float MaxSim (a-7)
+def test_bf16_config0_shape_single_query():
+    # BASELINE config 0: 100 pages x 1024 patches x 128-d, one 32-token query
+    rng = np.random.default_rng(1234)
+    pages = make_pages(rng, [1024] * 100)
+    q = [unit_rows(np.random.default_rng(4321), 32)]
+    idx = MaxSimIndex(dtype="bf16")
+    idx.add_pages(pages)
+    got = idx.score_matrix(q)
+    want = oracle_float(q, pages)
+    assert_close_rel(got, want, 2e-5)  # same bf16-rounded inputs, fp32 accumulate: only summation order differs
+    want_fp32 = oracle_float(q, pages, bf16=False)  # vs the reference's fp32 inputs: bf16 storage error only
+    assert_close_rel(got, want_fp32, BF16_RTOL)
+    ts, ti, tc = idx.search_host(q, k=10)
+    os_, oi = orc.topk_np(want[0], 10)
+    assert tc[0] == 10 and ti[0].tolist() == oi.tolist()
+    np.testing.assert_allclose(ts[0], os_, rtol=2e-5)
+
+
+def test_bf16_golden_fixture_from_score_multi_vector(golden_dir):
+    fm = np.load(os.path.join(golden_dir, "float_maxsim.npz"))
+    # case D is bf16-valued (what ColQwen emits), so bf16 storage is lossless and the port's scores are the target
+    idx = MaxSimIndex(dtype="bf16")
+    idx.add_pages(list(fm["d_pages"]))
+    got = idx.score_matrix([fm["d_q"]])
+    np.testing.assert_allclose(got[0], fm["d_scores"][0], rtol=2e-5, atol=1e-5)
+    # case A (fp32-valued, equal lengths): within the bf16 tolerance of the port's fp32 result
+    idx2 = MaxSimIndex(dtype="bf16")
+    idx2.add_pages(list(fm["a_pages"]))
+    got2 = idx2.score_matrix([fm["a_q0"], fm["a_q1"]])
+    assert_close_rel(got2, fm["a_scores"], BF16_RTOL)
+
+
+@pytest.mark.parametrize("unit_rows_", [0, 64, 1000])
+def test_bf16_ragged_pages_empty_pages_unit_boundaries(unit_rows_):
+    rng = np.random.default_rng(7)
+    lens = [1, 31, 32, 33, 0, 64, 127, 128, 129, 5, 700, 1030, 0, 2, 96, 255, 256, 257, 40, 1] + list(
+        rng.integers(1, 300, size=60))
+    pages = make_pages(rng, lens)
+    queries = [unit_rows(rng, 32), unit_rows(rng, 7), -np.abs(unit_rows(rng, 20))]  # last: all-negative dots possible
+    idx = MaxSimIndex(dtype="bf16")
+    if unit_rows_:
+        idx.set_tuning(unit_rows=unit_rows_)
+    idx.add_pages(pages[:30])
+    idx.add_pages(pages[30:])  # incremental append
+    got = idx.score_matrix(queries)
+    want = oracle_float(queries, pages)
+    assert_close_rel(got, want, 2e-5)
+    assert np.all(got[:, [4, 12]] == 0.0)  # empty pages score exactly 0
+
+
+@pytest.mark.parametrize("n_q,t", [(2, 32), (3, 32), (5, 17), (8, 32), (16, 32), (32, 32), (33, 20), (1, 70), (2, 1030)])
+def test_bf16_query_batches_and_long_queries(n_q, t):
+    rng = np.random.default_rng(100 + n_q * 7 + t)
+    lens = list(rng.integers(20, 200, size=40)) + [1024, 1024]
+    pages = make_pages(rng, lens)
+    queries = [unit_rows(rng, t if i % 2 == 0 else max(1, t - 3)) for i in range(n_q)]
+    idx = MaxSimIndex(dtype="bf16")
+    idx.set_tuning(unit_rows=512)
+    idx.add_pages(pages)
+    got = idx.score_matrix(queries)
+    want = oracle_float(queries, pages)
+    assert_close_rel(got, want, 3e-5)
+    k = 7
+    ts, ti, tc = idx.search_host(queries, k=k)
+    for q in range(n_q):
+        _, oi = orc.topk_np(want[q], k)
+        assert ti[q].tolist() == oi.tolist(), f"query {q}"
+
+
+# ------------------------------------------------------------------------------------------------ int8 MaxSim (config 3)
+@pytest.mark.parametrize("n_q", [1, 4, 9, 32])
+def test_int8_bit_exact(n_q):
+    rng = np.random.default_rng(11 + n_q)
+    lens = [1, 33, 0, 64, 200, 1024, 17, 96] + list(rng.integers(1, 260, size=30))
+    pages = make_pages(rng, lens)
+    queries = [unit_rows(rng, 32 if i % 3 else 19) for i in range(n_q)]
+    idx = MaxSimIndex(dtype="int8", i8_scale=127.0)
+    idx.set_tuning(unit_rows=256)
+    idx.add_pages(pages)
+    scores, goff, n_pages, _ = idx.score_groups(queries)
+    torch.cuda.synchronize()
+    raw = scores[:, :n_pages].cpu().numpy().astype(np.int64)
+    rows_q = orc.quantize_int8_np(np.concatenate(pages), 127.0)
+    # the packed corpus holds exactly the oracle's quantisation (rint half-even, clamp)
+    packed = idx.packed_rows().cpu().numpy().view(np.int8)
+    off_pad = np.concatenate([[0], np.cumsum([(n + 31) // 32 * 32 for n in lens])])
+    off = orc.page_offsets(lens)
+    for p in (0, 1, 5, 7):
+        assert np.array_equal(packed[off_pad[p]:off_pad[p] + lens[p]], rows_q[off[p]:off[p + 1]])
+    for qi, q in enumerate(queries):
+        want = orc.int8_maxsim_c(orc.quantize_int8_np(q, 127.0), rows_q, off)
+        got = raw[goff[qi]:goff[qi + 1]].sum(axis=0)
+        assert np.array_equal(got, want), f"query {qi}"  # integer arithmetic: bit-exact
+    ts, ti, tc = idx.search_host(queries, k=5)
+    for qi, q in enumerate(queries):
+        want = orc.int8_maxsim_c(orc.quantize_int8_np(q, 127.0), rows_q, off)
+        _, oi = orc.topk_np(want, 5)
+        assert ti[qi].tolist() == oi.tolist()
+
+
+# ------------------------------------------------------------------------------------------------ binary MaxSim (a-3, a-4)
+def test_binary_known_answers_from_reference_tests(golden_dir):
+    kn = np.load(os.path.join(golden_dir, "binary_known.npz"))
+    idx = MaxSimIndex(dtype="binary")
+    idx.add_pages([kn["pattern_rows"][:3], kn["pattern_rows"][3:]])
+    ts, ti, tc = idx.search_host([kn["pattern_query"]], k=2)
+    assert ti[0].tolist() == [0, 1] and ts[0].tolist() == [1.0, 0.0]  # test_multivector.py:222-256
+    rng = np.random.default_rng(3)
+    pages = [rng.uniform(-1, 1, size=(3, 128)).astype(np.float32) for _ in range(9)]
+    idx2 = MaxSimIndex(dtype="binary")
+    idx2.add_pages(pages)
+    for j in (0, 4, 8):  # self-match is top-1 with score exactly T (test_multivector.py:166-177)
+        ts, ti, tc = idx2.search_host([pages[j]], k=9)
+        assert ti[0][0] == j and ts[0][0] == 3.0 and np.all(np.diff(ts[0]) <= 0)
+
+
+@pytest.mark.parametrize("n_q", [1, 3, 8, 13])
+def test_binary_bit_exact(n_q):
+    rng = np.random.default_rng(50 + n_q)
+    lens = [1, 31, 32, 33, 0, 64, 1024, 5, 700] + list(rng.integers(1, 200, size=50))
+    pages = make_pages(rng, lens)
+    queries = [unit_rows(rng, t) for t in ([32, 7, 45, 1, 20, 64, 33, 32, 2, 9, 100, 31, 32][:n_q])]
+    idx = MaxSimIndex(dtype="binary")
+    idx.add_pages(pages)
+    got = idx.score_matrix(queries)
+    d_bits = orc.sign_pack_c(np.concatenate(pages))
+    off = orc.page_offsets(lens)
+    for qi, q in enumerate(queries):
+        want, want_int = orc.binary_maxsim_c(orc.sign_pack_c(q), d_bits, off)
+        assert np.array_equal(got[qi], want), f"query {qi}"  # multiples of 1/128: exact
+    ts, ti, tc = idx.search_host(queries, k=6)
+    for qi, q in enumerate(queries):
+        want, _ = orc.binary_maxsim_c(orc.sign_pack_c(q), d_bits, off)
+        os_, oi = orc.topk_np(want, 6)
+        assert ti[qi].tolist() == oi.tolist() and np.array_equal(ts[qi].astype(np.float64), os_)
+
+
+# ------------------------------------------------------------------------------------------------ top-k / filter
+def test_topk_ties_mask_and_short_lists():
+    rng = np.random.default_rng(9)
+    # binary scores are multiples of 1/128 -> many exact ties: the tie rule (lower page id first) must hold
+    pages = [np.sign(rng.standard_normal((4, 128))).astype(np.float32) for _ in range(300)]
+    pages += [pages[3].copy(), pages[3].copy()]  # exact duplicates of page 3 at ids 300, 301
+    q = [pages[3][:2]]
+    idx = MaxSimIndex(dtype="binary")
+    idx.add_pages(pages)
+    d_bits = orc.sign_pack_c(np.concatenate(pages))
+    off = orc.page_offsets([4] * len(pages))
+    want, _ = orc.binary_maxsim_c(orc.sign_pack_c(q[0]), d_bits, off)
+    for k in (1, 3, 50, 302, 400):
+        ts, ti, tc = idx.search_host(q, k=k)
+        os_, oi = orc.topk_np(want, k)
+        n = min(k, len(pages))
+        assert tc[0] == n and ti[0][:n].tolist() == oi.tolist()
+        assert np.all(ti[0][n:] == -1) and np.all(np.isinf(ts[0][n:]))
+    assert ti[0][:3].tolist() == [3, 300, 301]
+    allowed = rng.random(len(pages)) < 0.3
+    allowed[3] = False
+    allowed[300] = True
+    ts, ti, tc = idx.search_host(q, k=20, allow_mask=idx.mask_from_pages(allowed))
+    os_, oi = orc.topk_np(want, 20, allowed)
+    assert ti[0].tolist() == oi.tolist() and ti[0][0] == 300
+    none = np.zeros(len(pages), dtype=bool)
+    ts, ti, tc = idx.search_host(q, k=5, allow_mask=idx.mask_from_pages(none))
+    assert tc[0] == 0 and np.all(ti[0] == -1)
+
+
+def test_topk_large_k_and_many_pages_bf16():
+    rng = np.random.default_rng(21)
+    pages = make_pages(rng, [32] * 5000)
+    queries = [unit_rows(rng, 32) for _ in range(3)]
+    idx = MaxSimIndex(dtype="bf16")
+    idx.add_pages(pages)
+    got = idx.score_matrix(queries)
+    for k in (1000, 4096):
+        ts, ti, tc = idx.search_host(queries, k=k)
+        for q in range(3):
+            # compare against a ranking of the GPU's own scores (isolates the selection from fp rounding)
+            os_, oi = orc.topk_np(got[q].astype(np.float32), k)
+            assert ti[q].tolist() == oi.tolist()
+            np.testing.assert_array_equal(ts[q], os_.astype(np.float32))
+
+
+def test_merge_topk_matches_oracle():
+    rng = np.random.default_rng(33)
+    idx = MaxSimIndex(dtype="bf16")
+    n_q, m, k = 5, 800, 100
+    s = rng.standard_normal((n_q, m)).astype(np.float32)
+    s[:, 100:140] = s[:, 0:40]  # ties across "shards"
+    ids = np.stack([rng.permutation(100000)[:m] for _ in range(n_q)]).astype(np.int64)
+    ids[:, -17:] = -1  # unused slots
+    ts, ti, tc = idx.merge_topk(torch.from_numpy(s).cuda(), torch.from_numpy(ids).cuda(), k)
+    ts, ti = ts.cpu().numpy(), ti.cpu().numpy()
+    for q in range(n_q):
+        valid = ids[q] >= 0
+        order = np.lexsort((ids[q][valid], -s[q][valid].astype(np.float64)))[:k]
+        assert ti[q].tolist() == ids[q][valid][order].tolist()
+        np.testing.assert_array_equal(ts[q], s[q][valid][order])
+
+
+# ------------------------------------------------------------------------------------------------ size-independent properties
+def test_properties_at_scale_bf16():
+    """At a size the oracle cannot sweep in seconds (16k pages x 1024 patches, 4 GiB bf16), check invariants of MaxSim."""
+    n_pages, p = 16384, 1024
+    g = torch.Generator(device="cuda").manual_seed(1234)
+    rows = torch.randn((n_pages * p, 128), generator=g, device="cuda", dtype=torch.float32)
+    rows = torch.nn.functional.normalize(rows, dim=1).to(torch.bfloat16)
+    qg = torch.Generator(device="cuda").manual_seed(4321)
+    q = torch.nn.functional.normalize(torch.randn((32, 128), generator=qg, device="cuda"), dim=1)
+    # plant: page 777's first 32 rows are the query tokens themselves -> score ~ 32 (the maximum), rank 1
+    rows[777 * p: 777 * p + 32] = q.to(torch.bfloat16)
+    # duplicate page 5 into page 9000 -> identical scores; reverse the row order of page 42 into page 43 -> identical
+    rows[9000 * p:9001 * p] = rows[5 * p:6 * p]
+    rows[43 * p:44 * p] = rows[42 * p:43 * p].flip(0)
+    buf = torch.empty(rows.numel() * 2 + 1024, dtype=torch.uint8, device="cuda")
+    off = (-buf.data_ptr()) % 1024
+    packed = buf[off:off + rows.numel() * 2]
+    packed.copy_(rows.view(torch.uint8).reshape(-1))
+    idx = MaxSimIndex(dtype="bf16")
+    idx.adopt_packed(packed, [p] * n_pages)
+    qn = q.cpu().numpy()
+    s = idx.score_matrix([qn])[0]
+    assert s.argmax() == 777 and abs(s[777] - 32.0) < 0.05
+    assert s[9000] == s[5] and s[43] == s[42]
+    # oracle on a bounded sample of pages (every 512th + the special ones)
+    sample = sorted(set(range(0, n_pages, 512)) | {5, 42, 43, 777, 9000})
+    rows_h = torch.stack([rows[i * p:(i + 1) * p].float().cpu() for i in sample]).numpy().reshape(-1, 128)
+    want = orc.float_maxsim_c(orc.bf16_round_np(qn), rows_h, orc.page_offsets([p] * len(sample)))
+    assert_close_rel(s[sample], want, 2e-5)
+    # linearity in the query scale: scoring 2q doubles every score exactly (power-of-two scaling is exact in bf16/fp32)
+    s2 = idx.score_matrix([2.0 * qn])[0]
+    assert np.array_equal(s2, 2.0 * s)
+    # batch consistency: the same query inside a 32-query batch (NM=4, two passes) gives the same scores
+    others = [torch.nn.functional.normalize(torch.randn((32, 128), generator=qg, device="cuda"), dim=1).cpu().numpy() for _ in range(31)]
+    sb = idx.score_matrix([qn] + others)
+    assert np.array_equal(sb[0], s)
+    ts, ti, tc = idx.search_host([qn] + others, k=10)
+    assert ti[0][0] == 777
+    for qi in range(32):
+        _, oi = orc.topk_np(sb[qi].astype(np.float32), 10)
+        assert ti[qi].tolist() == oi.tolist()

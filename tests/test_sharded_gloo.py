@@ -1,0 +1,114 @@
+"""World-size-2 test of the multi-GPU host logic on CPU (gloo): shard plan, exchange-buffer packing, the single
+all-gather, and the merge order.  Local search and merge are oracle-backed test doubles (the product injects the CUDA
+MaxSimIndex methods instead -- morphik-core_b200/sharded.py:ShardedMaxSim.from_index)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from morphik_core_b200.sharded import ShardedMaxSim, pack_exchange, plan_document_shards, unpack_exchange
+from oracle import maxsim_oracle as orc
+
+
+def test_plan_document_shards_balanced_and_contiguous():
+    rows = [1024] * 100
+    plan = plan_document_shards(rows, 8)
+    assert plan[0][0] == 0 and plan[-1][1] == 100 and all(a[1] == b[0] for a, b in zip(plan, plan[1:]))
+    sizes = [e - b for b, e in plan]
+    assert max(sizes) - min(sizes) <= 1
+    rng = np.random.default_rng(0)
+    rows = rng.integers(1, 5000, size=997).tolist()
+    plan = plan_document_shards(rows, 4)
+    tot = [sum(rows[b:e]) for b, e in plan]
+    assert sum(tot) == sum(rows) and max(tot) - min(tot) <= 5000
+    assert plan_document_shards([10, 10], 4)[-1][1] == 2  # fewer documents than ranks: some ranges are empty
+    assert plan_document_shards([], 2) == [(0, 0), (0, 0)]
+
+
+def test_pack_unpack_exchange_roundtrip():
+    ids = torch.arange(24, dtype=torch.int64).reshape(2, 3, 4)  # [world, n_q, k]
+    sc = torch.arange(24, dtype=torch.float32).reshape(2, 3, 4) * 0.5
+    bufs = torch.stack([pack_exchange(ids[w], sc[w]) for w in range(2)])
+    ci, cs = unpack_exchange(bufs.reshape(-1), 2, 3, 4)
+    assert ci.shape == (3, 8) and ci[1].tolist() == ids[0, 1].tolist() + ids[1, 1].tolist()
+    assert cs[2].tolist() == sc[0, 2].tolist() + sc[1, 2].tolist()
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _oracle_merge(cand_scores, cand_ids, k):
+    n_q = cand_scores.shape[0]
+    ts = torch.full((n_q, k), float("-inf"))
+    ti = torch.full((n_q, k), -1, dtype=torch.int64)
+    tc = torch.zeros(n_q, dtype=torch.int32)
+    for q in range(n_q):
+        ids, s = cand_ids[q].numpy(), cand_scores[q].numpy()
+        valid = ids >= 0
+        order = np.lexsort((ids[valid], -s[valid].astype(np.float64)))[:k]
+        ts[q, :len(order)] = torch.from_numpy(s[valid][order])
+        ti[q, :len(order)] = torch.from_numpy(ids[valid][order])
+        tc[q] = len(order)
+    return ts, ti, tc
+
+
+def _worker(rank, world, port, k, result_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(77)  # same corpus description on every rank
+        doc_pages = rng.integers(1, 6, size=23).tolist()  # pages per document
+        page_lens = [int(x) for x in rng.integers(1, 70, size=sum(doc_pages))]
+        pages = [rng.standard_normal((n, 128)).astype(np.float32) for n in page_lens]
+        queries = [rng.standard_normal((t, 128)).astype(np.float32) for t in (32, 9, 40)]
+        doc_first_page = np.concatenate([[0], np.cumsum(doc_pages)])
+        doc_rows = [sum(page_lens[doc_first_page[d]:doc_first_page[d + 1]]) for d in range(len(doc_pages))]
+        plan = plan_document_shards(doc_rows, world)
+        p0, p1 = int(doc_first_page[plan[rank][0]]), int(doc_first_page[plan[rank][1]])
+        my_pages, my_lens = pages[p0:p1], page_lens[p0:p1]
+
+        def local_search(q, q_lens, kk):  # oracle-backed stand-in for MaxSimIndex.search_device(id_base=p0)
+            ts = torch.full((len(q_lens), kk), float("-inf"))
+            ti = torch.full((len(q_lens), kk), -1, dtype=torch.int64)
+            rows = np.concatenate(my_pages) if my_pages else np.zeros((0, 128), np.float32)
+            off = orc.page_offsets(my_lens)
+            qoff = np.concatenate([[0], np.cumsum(q_lens)])
+            for qi in range(len(q_lens)):
+                s = orc.float_maxsim_c(q[qoff[qi]:qoff[qi + 1]].numpy(), rows, off)
+                a, b = orc.topk_np(s, kk)
+                ts[qi, :len(a)] = torch.from_numpy(a.astype(np.float32))
+                ti[qi, :len(b)] = torch.from_numpy(b + p0)
+            return ts, ti
+
+        sharded = ShardedMaxSim(local_search, _oracle_merge)
+        q = torch.from_numpy(np.concatenate(queries))
+        if rank != 0:
+            q = torch.zeros_like(q)
+        q = sharded.broadcast_queries(q, src=0)
+        ts, ti, tc = sharded.search(q, [len(x) for x in queries], k)
+        # every rank must hold the global answer
+        rows = np.concatenate(pages)
+        off = orc.page_offsets(page_lens)
+        for qi, qq in enumerate(queries):
+            want_s, want_i = orc.topk_np(orc.float_maxsim_c(qq, rows, off), k)
+            n = len(want_i)  # k may exceed the number of pages: unused slots are -1 / -inf
+            assert int(tc[qi]) == n and ti[qi][:n].tolist() == want_i.tolist(), (rank, qi)
+            assert torch.all(ti[qi][n:] == -1)
+            np.testing.assert_allclose(ts[qi][:n].numpy(), want_s, rtol=1e-6)
+        open(os.path.join(result_dir, f"ok{rank}"), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("k", [5, 200])
+def test_sharded_search_world2_gloo(tmp_path, k):
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), k, str(tmp_path)), nprocs=world, join=True)
+    assert sorted(os.listdir(tmp_path)) == ["ok0", "ok1"]

@@ -1,0 +1,116 @@
+"""Host logic of the plugin (no GPU): the catalogue, the doc_ids/app_id filter, tombstones + compaction, and the
+B200MultiVectorStore contract (core/vector_store/base_vector_store.py:7-65) exercised with an injected index whose
+scores come from the oracle -- test wiring only; the product always constructs the CUDA MaxSimIndex."""
+import asyncio
+
+import numpy as np
+import pytest
+
+from morphik_core_b200.catalog import PageCatalog, PageRecord
+from morphik_core_b200.models import DocumentChunk
+from morphik_core_b200.store import B200MultiVectorStore, as_query_matrix, build_store_metrics
+from oracle import maxsim_oracle as orc
+
+
+class OracleIndex:
+    """Stands in for MaxSimIndex in host-logic tests (binary semantics = the Postgres provider)."""
+
+    row_bytes = 16
+
+    def __init__(self):
+        self.pages = []
+
+    def add_pages(self, pages):
+        first = len(self.pages)
+        self.pages.extend(np.asarray(p, np.float32) for p in pages)
+        return first, len(pages)
+
+    def compact(self, keep):
+        self.pages = [self.pages[int(i)] for i in keep]
+
+    def search_host(self, queries, k, allow_mask=None):
+        lens = [len(p) for p in self.pages]
+        d = orc.sign_pack_c(np.concatenate(self.pages)) if sum(lens) else np.zeros((0, 16), np.uint8)
+        off = orc.page_offsets(lens)
+        ts = np.full((len(queries), k), -np.inf, np.float32)
+        ti = np.full((len(queries), k), -1, np.int64)
+        tc = np.zeros(len(queries), np.int32)
+        for qi, q in enumerate(queries):
+            s, _ = orc.binary_maxsim_c(orc.sign_pack_c(q), d, off)
+            a, b = orc.topk_c(s, k, allow_mask)
+            ts[qi, :len(a)], ti[qi, :len(b)], tc[qi] = a, b, len(a)
+        return ts, ti, tc
+
+
+def run(coro):
+    return asyncio.run(coro)
+
+
+def chunk(doc, num, emb, content="c", meta=None):
+    return DocumentChunk(document_id=doc, chunk_number=num, content=content, embedding=emb, metadata=meta or {})
+
+
+def test_catalog_mask_delete_compact():
+    cat = PageCatalog()
+    for d, n in [("a", 0), ("a", 1), ("b", 0), ("c", 0), ("c", 1), ("c", 2)]:
+        cat.add(PageRecord(d, n, f"{d}{n}", {}, app_id="app1" if d != "b" else None, n_rows=3))
+    assert len(cat) == 6 and cat.allow_mask() is None
+    assert cat.allow_mask(["a", "zzz"]).tolist() == [1, 1, 0, 0, 0, 0]
+    assert cat.allow_mask([]).tolist() == [0] * 6
+    assert cat.allow_mask(None, app_id="other").tolist() == [0, 0, 1, 0, 0, 0]  # only the app-less page is visible
+    assert cat.allow_mask(None, app_id="app1") is None
+    words = PageCatalog.mask_words(np.array([1, 0, 1] + [0] * 30 + [1], dtype=bool))
+    assert words.tolist() == [0b101, 0b10]
+    assert cat.delete_document("a") == [0, 1] and cat.n_live == 4 and cat.lookup("a", 1) is None
+    assert cat.allow_mask().tolist() == [0, 0, 1, 1, 1, 1]
+    keep, remap = cat.compaction_plan()
+    assert keep.tolist() == [2, 3, 4, 5] and remap.tolist() == [-1, -1, 0, 1, 2, 3]
+    cat.apply_compaction(keep)
+    assert len(cat) == 4 and cat.lookup("c", 2) == 3 and cat.pages_of("b") == [0]
+
+
+def test_as_query_matrix_accepts_reference_input_forms():
+    import torch
+
+    q = np.random.default_rng(0).standard_normal((5, 128)).astype(np.float32)
+    for form in (q, torch.from_numpy(q), [r for r in q], [torch.from_numpy(r) for r in q], q.tolist(), q.astype(np.float64)):
+        np.testing.assert_array_equal(as_query_matrix(form), q)
+    assert as_query_matrix(q[0]).shape == (1, 128)
+    with pytest.raises(ValueError):
+        as_query_matrix(np.zeros((3, 64)))
+
+
+def test_store_contract_matches_reference_tests():
+    store = B200MultiVectorStore(auto_initialize=False, index=OracleIndex(), compact_dead_fraction=0.3)
+    # test_multivector.py:206-211: empty list
+    assert run(store.store_embeddings([])) == (True, [], build_store_metrics())
+    # test_multivector.py:214-256: pattern page ranks first
+    e1 = np.ones((3, 128)); e1[:, 64:] = -1
+    e2 = -e1
+    ok, ids, metrics = run(store.store_embeddings([chunk("similarity_test_1", 1, e1), chunk("similarity_test_2", 2, e2)]))
+    assert ok and ids == ["similarity_test_1-1", "similarity_test_2-2"] and metrics["vector_store_rows"] == 2
+    qe = np.ones(128); qe[64:] = -1
+    res = run(store.query_similar(np.array([qe]), k=2))
+    assert [r.document_id for r in res] == ["similarity_test_1", "similarity_test_2"]
+    assert [r.score for r in res] == [1.0, 0.0] and all(r.embedding == [] for r in res)
+    # test_multivector.py:184-202: doc_ids filter
+    res = run(store.query_similar(np.array([qe]), k=5, doc_ids=["similarity_test_2"]))
+    assert [r.document_id for r in res] == ["similarity_test_2"]
+    assert run(store.query_similar(np.array([qe]), k=5, doc_ids=["nope"])) == []
+    # test_multivector.py:259-294: metadata round trip + get_chunks_by_id
+    run(store.store_embeddings([chunk("meta_doc", 7, e1, content="payload", meta={"page": 7, "is_image": True})], app_id="app"))
+    got = run(store.get_chunks_by_id([("meta_doc", 7), ("meta_doc", 7), ("missing", 0)]))
+    assert len(got) == 1 and got[0].metadata == {"page": 7, "is_image": True} and got[0].content == "payload" and got[0].score == 0.0
+    assert run(store.get_chunks_by_id([("meta_doc", 7)], app_id="other")) == []
+    # chunks without embeddings are skipped (multi_vector_store.py:632-636)
+    ok, ids, _ = run(store.store_embeddings([chunk("noemb", 0, None)]))
+    assert ok and ids == []
+    # delete + automatic compaction keep ids and scores consistent
+    assert run(store.delete_chunks_by_document_id("similarity_test_1")) is True
+    res = run(store.query_similar(np.array([qe]), k=5))
+    assert [r.document_id for r in res] == ["meta_doc", "similarity_test_2"] and res[0].score == 1.0
+    assert len(store.catalog) == 2  # compaction ran (1/3 dead > 0.3)
+    assert run(store.delete_chunks_by_document_id("never_existed")) is True
+    # batched extension returns one list per query, k larger than the corpus is fine
+    out = run(store.query_similar_batch([np.array([qe]), np.array([-qe])], k=10))
+    assert [len(o) for o in out] == [2, 2] and out[1][0].document_id == "similarity_test_2"
