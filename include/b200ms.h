@@ -146,6 +146,11 @@ int64_t b200ms_launch_count(const b200ms_t* h);
 /* Device time (ms, CUDA events on the launching stream) of the last b200ms_score call's scoring kernels only;
  * synchronises.  Returns a negative error code on failure. */
 float b200ms_last_score_ms(b200ms_t* h);
+/* Number of scoring calls (b200ms_score or search) recorded so far, and the device times (ms) of the most recent n of
+ * them (n <= 256, oldest first; synchronises; returns n or a negative error).  bench.py derives the roofline's
+ * `achieved` from these: CUDA events on the launching stream, recorded inside the timed region. */
+int64_t b200ms_score_call_count(const b200ms_t* h);
+int b200ms_score_times_ms(b200ms_t* h, float* out_ms, int n);
 /* Tuning knobs (0 keeps the default): rows per work unit, CTAs to launch. */
 int b200ms_set_tuning(b200ms_t* h, int64_t unit_rows, int max_ctas);
 

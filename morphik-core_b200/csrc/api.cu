@@ -150,8 +150,10 @@ B200MS_API int b200ms_create(int device, b200ms_t** out) {
     delete h;
     return e;
   }
-  cudaEventCreate(&h->ev0);
-  cudaEventCreate(&h->ev1);
+  for (int i = 0; i < b200ms::kEvRing; ++i) {
+    cudaEventCreate(&h->ev0[i]);
+    cudaEventCreate(&h->ev1[i]);
+  }
   *out = h;
   return B200MS_OK;
 }
@@ -165,8 +167,10 @@ B200MS_API int b200ms_destroy(b200ms_t* h) {
   for (DeviceBuf* b : bufs)
     if (b->p) cudaFree(b->p);
   if (h->pinned) cudaFreeHost(h->pinned);
-  if (h->ev0) cudaEventDestroy(h->ev0);
-  if (h->ev1) cudaEventDestroy(h->ev1);
+  for (int i = 0; i < b200ms::kEvRing; ++i) {
+    if (h->ev0[i]) cudaEventDestroy(h->ev0[i]);
+    if (h->ev1[i]) cudaEventDestroy(h->ev1[i]);
+  }
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return B200MS_OK;
@@ -335,8 +339,8 @@ static int score_impl(b200ms_t* h, const void* q_packed, int n_groups, const int
   if (c.dtype < 0) return set_error(h, B200MS_ESTATE, "score: no corpus attached (call b200ms_set_corpus first)");
   if (n_groups < 0 || ld < c.n_pages || (n_groups > 0 && (!q_packed || !group_scores)))
     return set_error(h, B200MS_EINVAL, "score: bad arguments");
-  h->ev_valid = false;
   if (n_groups == 0 || c.n_pages == 0) return B200MS_OK;
+  const int slot = int(h->ev_count % b200ms::kEvRing);
   const int n_groups_padded = (n_groups + 3) & ~3;
   if (c.dtype == B200MS_B1) {
     if (!q_lens || !group_offsets || n_q <= 0) return set_error(h, B200MS_EINVAL, "score: B1 needs q_lens and group_offsets");
@@ -349,10 +353,10 @@ static int score_impl(b200ms_t* h, const void* q_packed, int n_groups, const int
       }
     }
     if (int e = upload(h, h->meta_c, ntok.data(), ntok.size() * 4, s)) return e;
-    cudaEventRecord(h->ev0, s);
+    cudaEventRecord(h->ev0[slot], s);
     if (int e = launch_score_b1(h, q_packed, n_groups, static_cast<const int32_t*>(h->meta_c.p), group_scores, ld, s)) return e;
-    cudaEventRecord(h->ev1, s);
-    h->ev_valid = true;
+    cudaEventRecord(h->ev1[slot], s);
+    h->ev_count++;
     // ntok is pageable host memory: the async upload staged it before returning, nothing else to wait for
     return B200MS_OK;
   }
@@ -360,10 +364,10 @@ static int score_impl(b200ms_t* h, const void* q_packed, int n_groups, const int
   if (c.has_empty) {
     if (int e = check_cuda(h, cudaMemsetAsync(group_scores, 0, size_t(n_groups_padded) * size_t(ld) * 4, s), "score: memset")) return e;
   }
-  cudaEventRecord(h->ev0, s);
+  cudaEventRecord(h->ev0[slot], s);
   if (int e = launch_score_umma(h, q_packed, n_groups, group_scores, ld, s)) return e;
-  cudaEventRecord(h->ev1, s);
-  h->ev_valid = true;
+  cudaEventRecord(h->ev1[slot], s);
+  h->ev_count++;
   return B200MS_OK;
 }
 
@@ -374,14 +378,31 @@ B200MS_API int b200ms_score(b200ms_t* h, const void* q_packed, int n_groups, con
   return score_impl(h, q_packed, n_groups, q_lens, group_offsets, n_q, group_scores, ld, static_cast<cudaStream_t>(stream));
 }
 
+static int score_time_of(b200ms_t* h, int64_t idx, float* ms) {
+  const int slot = int(idx % b200ms::kEvRing);
+  if (cudaEventSynchronize(h->ev1[slot]) != cudaSuccess) return check_cuda(h, cudaGetLastError(), "cudaEventSynchronize");
+  if (cudaEventElapsedTime(ms, h->ev0[slot], h->ev1[slot]) != cudaSuccess) return check_cuda(h, cudaGetLastError(), "cudaEventElapsedTime");
+  return B200MS_OK;
+}
+
 B200MS_API float b200ms_last_score_ms(b200ms_t* h) {
   if (!h) return float(B200MS_EINVAL);
-  if (!h->ev_valid) return float(set_error(h, B200MS_ESTATE, "last_score_ms: no scoring call recorded"));
+  if (h->ev_count == 0) return float(set_error(h, B200MS_ESTATE, "last_score_ms: no scoring call recorded"));
   DeviceGuard g(h->device);
-  if (cudaEventSynchronize(h->ev1) != cudaSuccess) return float(check_cuda(h, cudaGetLastError(), "cudaEventSynchronize"));
   float ms = 0.f;
-  if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) != cudaSuccess) return float(check_cuda(h, cudaGetLastError(), "cudaEventElapsedTime"));
+  if (int e = score_time_of(h, h->ev_count - 1, &ms)) return float(e);
   return ms;
+}
+
+B200MS_API int64_t b200ms_score_call_count(const b200ms_t* h) { return h ? h->ev_count : 0; }
+
+B200MS_API int b200ms_score_times_ms(b200ms_t* h, float* out_ms, int n) {
+  if (!h || !out_ms || n < 0) return B200MS_EINVAL;
+  if (n > b200ms::kEvRing || n > h->ev_count) return set_error(h, B200MS_EINVAL, "score_times_ms: n exceeds the recorded history (ring of 256)");
+  DeviceGuard g(h->device);
+  for (int i = 0; i < n; ++i)
+    if (int e = score_time_of(h, h->ev_count - n + i, &out_ms[i])) return e;
+  return n;
 }
 
 B200MS_API int b200ms_topk(b200ms_t* h, const void* group_scores, int score_dtype, int64_t n_pages, int64_t ld,

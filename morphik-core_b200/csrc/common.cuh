@@ -50,8 +50,10 @@ struct b200ms {
   void* pinned = nullptr;  // pinned host staging
   size_t pinned_cap = 0;
   cudaStream_t stream = nullptr;  // internal stream for *_host entry points
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  bool ev_valid = false;
+  // ring of CUDA-event pairs bracketing the scoring kernels of the most recent b200ms_score / search calls
+  static constexpr int kEvRing = 256;
+  cudaEvent_t ev0[kEvRing] = {}, ev1[kEvRing] = {};
+  int64_t ev_count = 0;  // scoring calls recorded since creation / last reset
   int64_t launches = 0;
   int64_t unit_rows = 4096;
   int max_ctas = 0;

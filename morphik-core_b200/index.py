@@ -91,6 +91,14 @@ class MaxSimIndex:
             self.h.check(int(ms), "b200ms_last_score_ms")
         return ms
 
+    def score_times_ms(self, n: int) -> List[float]:
+        """Device times (ms) of the scoring kernels of the last n score/search calls (CUDA events on the launch stream)."""
+        buf = (ctypes.c_float * max(n, 1))()
+        rc = nat.lib.b200ms_score_times_ms(self.h.ptr, buf, int(n))
+        if rc < 0:
+            self.h.check(rc, "b200ms_score_times_ms")
+        return [float(buf[i]) for i in range(n)]
+
     def set_tuning(self, unit_rows: int = 0, max_ctas: int = 0):
         self.h.check(nat.lib.b200ms_set_tuning(self.h.ptr, int(unit_rows), int(max_ctas)), "b200ms_set_tuning")
         self._attached = False
