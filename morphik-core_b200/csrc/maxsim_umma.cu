@@ -145,45 +145,49 @@ maxsim_umma_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_c
     }
   } else if (warp == 1) {
     // ================================================================ MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc(KIND, kTileM, kTileN);
-      mbar_wait(qfull, 0);
-      tc_fence_after();
-      const uint32_t q_addr = smem_u32(smem_q);
-      const uint32_t st_addr = smem_u32(smem_st);
-      int stage = 0;
-      uint32_t phase = 0;
-      uint32_t seq = 0;
-      for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
-        const int c0 = __ldg(unit_start + u), c1 = __ldg(unit_start + u + 1);
-        const int n_tiles = (c1 - c0 + 3) >> 2;
-        for (int t = 0; t < n_tiles; ++t) {
-          mbar_wait(&full[stage], phase);
+    // The whole warp walks the loop (so every address/descriptor is warp-uniform and lives in uniform registers);
+    // only the tcgen05.mma / tcgen05.commit themselves are issued by the lane elect.sync picks.
+    constexpr uint32_t idesc = umma_idesc(KIND, kTileM, kTileN);
+    constexpr uint32_t kTileDesc = K::kTileBytes >> 4;  // tile size in descriptor units (16 B)
+    mbar_wait(qfull, 0);
+    tc_fence_after();
+    const uint64_t a_desc0 = umma_desc_kmajor_sw128(smem_u32(smem_q));
+    const uint64_t b_desc0 = umma_desc_kmajor_sw128(smem_u32(smem_st));
+    int stage = 0;
+    uint32_t phase = 0;
+    uint32_t seq = 0;
+    for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+      const int c0 = __ldg(unit_start + u), c1 = __ldg(unit_start + u + 1);
+      const int n_tiles = (c1 - c0 + 3) >> 2;
+      for (int t = 0; t < n_tiles; ++t) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        const uint64_t bd = b_desc0 + uint64_t(uint32_t(stage) * kTileDesc);
+#pragma unroll 1
+        for (int m = 0; m < NM; ++m, ++seq) {
+          const uint32_t buf = seq & (kNumAccum - 1);
+          mbar_wait(&tempty[buf], ((seq >> 2) & 1) ^ 1);
           tc_fence_after();
-          const uint32_t b_addr = st_addr + uint32_t(stage) * K::kTileBytes;
-#pragma unroll
-          for (int m = 0; m < NM; ++m, ++seq) {
-            const uint32_t buf = seq & (kNumAccum - 1);
-            mbar_wait(&tempty[buf], ((seq >> 2) & 1) ^ 1);
-            tc_fence_after();
+          if (elect_one()) {
             const uint32_t d_tmem = tmem_base + buf * kTileN;
-            const uint32_t a_addr = q_addr + uint32_t(m) * K::kTileBytes;
+            const uint64_t ad = a_desc0 + uint64_t(uint32_t(m) * kTileDesc);
 #pragma unroll
             for (int p = 0; p < K::kPanels; ++p) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {  // 4 x 32 B of K per 128 B panel
-                const uint64_t ad = umma_desc_kmajor_sw128(a_addr + p * kSubtileBytes + k * 32);
-                const uint64_t bd = umma_desc_kmajor_sw128(b_addr + p * kSubtileBytes + k * 32);
-                umma_ss<KIND>(d_tmem, ad, bd, idesc, (p | k) != 0);
+              for (int k = 0; k < 4; ++k) {  // 4 x 32 B of K per 128 B panel; +2 descriptor units per step
+                const uint32_t off = (p * kSubtileBytes + k * 32) >> 4;
+                umma_ss<KIND>(d_tmem, ad + off, bd + off, idesc, (p | k) != 0);
               }
             }
             umma_commit(&tfull[buf]);
           }
-          umma_commit(&empty[stage]);  // stage reusable once every query tile has consumed it
-          if (++stage == num_stages) {
-            stage = 0;
-            phase ^= 1;
-          }
+          __syncwarp();
+        }
+        if (elect_one()) umma_commit(&empty[stage]);  // stage reusable once every query tile has consumed it
+        __syncwarp();
+        if (++stage == num_stages) {
+          stage = 0;
+          phase ^= 1;
         }
       }
     }
@@ -194,7 +198,7 @@ maxsim_umma_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_c
     if (wg < NWG) {
       Acc runmax[NMW];
       int cur_page[NMW];
-      uint32_t seq = 0;
+      uint32_t tile_seq = 0;
       const uint32_t lane_base = tmem_base + (uint32_t(quad * 32) << 16);
 
       for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
@@ -203,19 +207,28 @@ maxsim_umma_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_c
 #pragma unroll
         for (int i = 0; i < NMW; ++i) cur_page[i] = -1;
 
-        for (int t = 0; t < n_tiles; ++t) {
+        for (int t = 0; t < n_tiles; ++t, ++tile_seq) {
           const int cb = c0 + 4 * t;
           int pg[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) pg[j] = (cb + j < c1) ? __ldg(chunk_page + cb + j) : -1;
 
-#pragma unroll
-          for (int m = 0; m < NM; ++m, ++seq) {
-            if (NWG == 2 && (m & 1) != wg) continue;
-            constexpr int kShift = NM == 1 ? 0 : 1;
-            const int mi = m >> kShift;
+          // one code copy for all owned query tiles (runtime loop): the per-tile state is moved in and out of the
+          // register arrays with compile-time-indexed selects, which keeps them out of local memory
+#pragma unroll 1
+          for (int i = 0; i < NMW; ++i) {
+            const int m = NM == 1 ? 0 : (2 * i + wg);
+            const uint32_t seq = tile_seq * NM + m;
             const uint32_t buf = seq & (kNumAccum - 1);
             const int group = (m_tile_base + m) * 4 + quad;
+            Acc rm = Acc(0);
+            int cp = -1;
+#pragma unroll
+            for (int j = 0; j < NMW; ++j)
+              if (j == i) {
+                rm = runmax[j];
+                cp = cur_page[j];
+              }
             mbar_wait(&tfull[buf], (seq >> 2) & 1);
             tc_fence_after();
             if (group < n_groups_real) {
@@ -238,15 +251,15 @@ maxsim_umma_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_c
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 if (pg[j] < 0) continue;  // chunk belongs to the next unit
-                if (pg[j] != cur_page[mi]) {
-                  if (cur_page[mi] >= 0) {
-                    const Acc s = warp_sum(runmax[mi]);
-                    if (lane == 0) group_scores[int64_t(group) * ld + cur_page[mi]] = s;
+                if (pg[j] != cp) {
+                  if (cp >= 0) {
+                    const Acc s = warp_sum(rm);
+                    if (lane == 0) group_scores[int64_t(group) * ld + cp] = s;
                   }
-                  cur_page[mi] = pg[j];
-                  runmax[mi] = cm[j];
+                  cp = pg[j];
+                  rm = cm[j];
                 } else {
-                  runmax[mi] = acc_max(runmax[mi], cm[j]);
+                  rm = acc_max(rm, cm[j]);
                 }
               }
             } else {
@@ -254,6 +267,12 @@ maxsim_umma_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_c
               __syncwarp();
               if (lane == 0) mbar_arrive(&tempty[buf]);
             }
+#pragma unroll
+            for (int j = 0; j < NMW; ++j)
+              if (j == i) {
+                runmax[j] = rm;
+                cur_page[j] = cp;
+              }
           }
         }
         // unit ends on a page boundary: flush the open page of every owned query tile
