@@ -40,6 +40,20 @@ METRIC = "patch_vectors_per_sec_maxsim"
 UNIT = "patch-vectors/s"
 
 
+def load_traffic():
+    """dram__bytes_read+write per patch vector of the dominant kernel, from the committed ncu --set full capture
+    (profiles/<round>/traffic.json, written by tools/ncu_summary.py); None if no capture is committed."""
+    best = None
+    pdir = os.path.join(ROOT, "profiles")
+    if os.path.isdir(pdir):
+        for rnd in sorted(os.listdir(pdir)):
+            path = os.path.join(pdir, rnd, "traffic.json")
+            if os.path.exists(path):
+                with open(path) as f:
+                    best = json.load(f)
+    return best
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -142,6 +156,10 @@ def cpu_reference_rate(n_q: int, budget_s: float, seed: int = 1234):
 
     from oracle import maxsim_oracle as orc
 
+    # torchrun exports OMP_NUM_THREADS=1; the reference arm is meant to use the host's cores (physical cores by default)
+    want = int(os.environ.get("B200MS_CPU_THREADS", "0")) or max(1, (os.cpu_count() or 2) // 2)
+    if torch.get_num_threads() != want:
+        torch.set_num_threads(want)
     q = make_queries(n_q).view(n_q, T_TOK, DIM).numpy()
     g = torch.Generator().manual_seed(seed)
 
@@ -318,11 +336,16 @@ def run_gpu(args):
     achieved_tf = flops_per_step / (score_ms_avg * 1e-3) / 1e12
     n_mtiles = (n_q * T_TOK + 127) // 128
     passes = (n_mtiles + 3) // 4
+    tr = load_traffic()
+    traffic_bytes = traffic_src = None
+    if tr and "maxsim_umma<bf16,NM=4>" in tr:
+        traffic_bytes = tr["maxsim_umma<bf16,NM=4>"]["dram_bytes_per_patch_vector"] * rows  # per launch (one pass)
+        traffic_src = tr["maxsim_umma<bf16,NM=4>"]["source"]
     roofline = {
         "kernel": "maxsim_umma_kernel<bf16,NM=4>", "bound": "tensor", "achieved": achieved_tf,
         "peak": peaks["tflops_sustained"], "unit": "TFLOP/s", "frac": achieved_tf / peaks["tflops_sustained"],
         "peak_kind": f"{peaks['source']} cuBLAS bf16 sustained (burst {peaks['tflops_burst']})",
-        "frac_of_burst": achieved_tf / peaks["tflops_burst"], "traffic": None,
+        "frac_of_burst": achieved_tf / peaks["tflops_burst"], "traffic": traffic_bytes, "traffic_source": traffic_src,
         "launches_per_step": passes, "avg_launch_ms": score_ms_avg / passes, "score_ms_per_step": score_ms_avg,
         "algorithmic_flops_per_launch": flops_per_step / passes,
         "hbm_gbs_in_this_regime": passes * rows * DIM * 2 / (score_ms_avg * 1e-3) / 1e9,
@@ -350,7 +373,9 @@ def run_gpu(args):
                "frac": gbs / peaks["hbm_gbs"], "peak_kind": f"{peaks['source']} copy bandwidth",
                "patch_vectors_per_sec": rows / (sm1_avg * 1e-3), "score_ms": sm1_avg,
                "step_ms": e0.elapsed_time(e1) / args.steps,
-               "algorithmic_bytes_per_launch": rows * DIM * 2}
+               "algorithmic_bytes_per_launch": rows * DIM * 2,
+               "traffic": (tr["maxsim_umma<bf16,NM=1>"]["dram_bytes_per_patch_vector"] * rows
+                           if tr and "maxsim_umma<bf16,NM=1>" in tr else None)}
 
     # ---- CPU baseline beside it (rank 0, N=1 only)
     cpu = None

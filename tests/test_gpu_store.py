@@ -1,0 +1,117 @@
+"""The reference's own store tests (core/tests/unit/test_multivector.py), re-run against B200MultiVectorStore on a GPU.
+Same scenarios and assertions; the Postgres fixture is replaced by the in-HBM store.  mode="binary" reproduces the Postgres
+provider's scores exactly; mode="bf16" the float MaxSim of the "morphik" provider."""
+import asyncio
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+if not torch.cuda.is_available():  # pragma: no cover
+    pytest.skip("CUDA device required", allow_module_level=True)
+
+from morphik_core_b200.models import DocumentChunk  # noqa: E402
+from morphik_core_b200.store import B200MultiVectorStore  # noqa: E402
+from oracle import maxsim_oracle as orc  # noqa: E402
+
+
+def run(coro):
+    return asyncio.run(coro)
+
+
+def get_sample_embeddings(num_vectors=3, dim=128, seed=0):  # test_multivector.py:23-34 (torch.rand * 2 - 1)
+    g = torch.Generator().manual_seed(seed)
+    return torch.rand((num_vectors, dim), generator=g) * 2 - 1
+
+
+@pytest.fixture(params=["binary", "bf16", "int8"])
+def vector_store(request):
+    store = B200MultiVectorStore(mode=request.param)
+    yield store
+    store.close()
+
+
+def test_store_embeddings_empty(vector_store):  # test_multivector.py:206-211
+    ok, ids, metrics = run(vector_store.store_embeddings([]))
+    assert ok is True and ids == [] and "vector_store_rows" in metrics
+
+
+def test_store_and_query_self_match(vector_store):  # test_multivector.py:152-181
+    chunks = [DocumentChunk(document_id=f"doc_{i}", content=f"Test content {i}", embedding=get_sample_embeddings(seed=i),
+                            chunk_number=i, metadata={"index": i}) for i in range(6)]
+    ok, ids, _ = run(vector_store.store_embeddings(chunks))
+    assert ok and ids == [f"doc_{i}-{i}" for i in range(6)]
+    results = run(vector_store.query_similar(get_sample_embeddings(seed=2), k=3))
+    assert len(results) == 3 and results[0].document_id == "doc_2"
+    assert all(results[i].score >= results[i + 1].score for i in range(2))
+    assert all(r.embedding == [] for r in results)
+    if vector_store.mode == "binary":
+        assert results[0].score == 3.0  # a 3-vector self query scores exactly T under SQL max_sim
+
+
+def test_query_with_doc_ids(vector_store):  # test_multivector.py:184-202
+    chunks = [DocumentChunk(document_id=f"doc_{i % 3}", content=f"c{i}", embedding=get_sample_embeddings(seed=10 + i),
+                            chunk_number=i, metadata={}) for i in range(9)]
+    run(vector_store.store_embeddings(chunks))
+    results = run(vector_store.query_similar(get_sample_embeddings(seed=99), k=9, doc_ids=["doc_0", "doc_2"]))
+    assert len(results) == 6 and {r.document_id for r in results} == {"doc_0", "doc_2"}
+    assert run(vector_store.query_similar(get_sample_embeddings(seed=99), k=9, doc_ids=["unknown"])) == []
+
+
+def test_multi_vector_similarity(vector_store):  # test_multivector.py:214-256
+    e1 = np.ones((3, 128)); e1[:, 64:] = -1
+    e2 = -np.ones((3, 128)); e2[:, 64:] = 1
+    run(vector_store.store_embeddings([
+        DocumentChunk(document_id="similarity_test_1", content="Similarity test content 1", embedding=e1, chunk_number=1),
+        DocumentChunk(document_id="similarity_test_2", content="Similarity test content 2", embedding=e2, chunk_number=2)]))
+    q = np.ones(128); q[64:] = -1
+    results = run(vector_store.query_similar(np.array([q]), k=2))
+    assert [r.document_id for r in results] == ["similarity_test_1", "similarity_test_2"]
+    if vector_store.mode == "binary":
+        assert [r.score for r in results] == [1.0, 0.0]
+    elif vector_store.mode == "bf16":
+        assert [r.score for r in results] == [128.0, -128.0]
+
+
+def test_store_and_retrieve_metadata(vector_store):  # test_multivector.py:259-294
+    meta = {"page": 3, "is_image": True, "nested": {"a": [1, 2]}}
+    run(vector_store.store_embeddings([DocumentChunk(document_id="metadata_test", content="payload", chunk_number=7,
+                                                     embedding=get_sample_embeddings(seed=5), metadata=meta)]))
+    res = run(vector_store.query_similar(get_sample_embeddings(seed=5), k=1))
+    assert res[0].metadata == meta and res[0].content == "payload" and res[0].chunk_number == 7
+    got = run(vector_store.get_chunks_by_id([("metadata_test", 7), ("metadata_test", 8)]))
+    assert len(got) == 1 and got[0].metadata == meta and got[0].score == 0.0
+
+
+def test_delete_and_compaction_keep_scores_consistent(vector_store):
+    rng = np.random.default_rng(0)
+    pages = {f"d{i}": [rng.standard_normal((int(rng.integers(1, 90)), 128)).astype(np.float32) for _ in range(3)] for i in range(8)}
+    for d, ps in pages.items():
+        run(vector_store.store_embeddings([DocumentChunk(document_id=d, content=d, embedding=p, chunk_number=j)
+                                           for j, p in enumerate(ps)], app_id="app"))
+    q = rng.standard_normal((20, 128)).astype(np.float32)
+    before = run(vector_store.query_similar(q, k=24))
+    for d in ("d1", "d2", "d5"):  # > 30 % dead -> compaction on the device
+        assert run(vector_store.delete_chunks_by_document_id(d)) is True
+    after = run(vector_store.query_similar(q, k=24))
+    expect = [(r.document_id, r.chunk_number, r.score) for r in before if r.document_id not in ("d1", "d2", "d5")]
+    assert [(r.document_id, r.chunk_number, r.score) for r in after] == expect
+    assert len(vector_store.catalog) == 15
+
+
+def test_binary_scores_equal_sql_max_sim_oracle():
+    store = B200MultiVectorStore(mode="binary")
+    rng = np.random.default_rng(3)
+    lens = [int(x) for x in rng.integers(1, 120, size=40)]
+    pages = [rng.standard_normal((n, 128)).astype(np.float32) for n in lens]
+    run(store.store_embeddings([DocumentChunk(document_id=f"doc{i // 4}", content="", embedding=p, chunk_number=i % 4)
+                                for i, p in enumerate(pages)]))
+    q = rng.standard_normal((32, 128)).astype(np.float32)
+    res = run(store.query_similar(q, k=40))
+    want, _ = orc.binary_maxsim_c(orc.sign_pack_c(q), orc.sign_pack_c(np.concatenate(pages)), orc.page_offsets(lens))
+    ws, wi = orc.topk_np(want, 40)
+    assert [(r.document_id, r.chunk_number) for r in res] == [(f"doc{i // 4}", i % 4) for i in wi]
+    assert [r.score for r in res] == ws.tolist()
+    store.close()
