@@ -57,6 +57,7 @@ def _load() -> ctypes.CDLL:
         "b200ms_launch_count": (c_int64, [vp]),
         "b200ms_last_score_ms": (c_float, [vp]),
         "b200ms_set_tuning": (c_int, [vp, c_int64, c_int]),
+        "b200ms_set_option": (c_int, [vp, c_char_p, c_int64]),
         "b200ms_score_call_count": (c_int64, [vp]),
         "b200ms_score_times_ms": (c_int, [vp, f32p, c_int]),
     }
@@ -74,7 +75,7 @@ EXPORTED = [
     "b200ms_pack_pages", "b200ms_set_corpus", "b200ms_corpus_pages", "b200ms_corpus_rows", "b200ms_pack_queries",
     "b200ms_score", "b200ms_topk", "b200ms_merge_topk", "b200ms_search_host", "b200ms_search_device",
     "b200ms_launch_count", "b200ms_last_score_ms", "b200ms_set_tuning", "b200ms_score_call_count",
-    "b200ms_score_times_ms",
+    "b200ms_score_times_ms", "b200ms_set_option",
 ]
 
 

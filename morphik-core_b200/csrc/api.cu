@@ -2,6 +2,7 @@
 // (chunk table, work-unit plan, TMA descriptor), query packing and the fused search entry points.
 // Host-side C++ only orchestrates; all arithmetic on embeddings happens in the CUDA kernels.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -146,6 +147,7 @@ B200MS_API int b200ms_create(int device, b200ms_t** out) {
   b200ms_t* h = new b200ms_t();
   h->device = device;
   h->num_sms = prop.multiProcessorCount;
+  if (const char* e = getenv("B200MS_A_IN_TMEM")) h->a_in_tmem = atoi(e) != 0;
   if (int e = check_cuda(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking), "cudaStreamCreate")) {
     delete h;
     return e;
@@ -206,6 +208,21 @@ B200MS_API int b200ms_set_tuning(b200ms_t* h, int64_t unit_rows, int max_ctas) {
   if (!h) return B200MS_EINVAL;
   if (unit_rows > 0) h->unit_rows = unit_rows;
   if (max_ctas >= 0) h->max_ctas = max_ctas;
+  return B200MS_OK;
+}
+
+B200MS_API int b200ms_set_option(b200ms_t* h, const char* name, int64_t value) {
+  if (!h || !name) return B200MS_EINVAL;
+  const std::string n(name);
+  if (n == "a_in_tmem") {
+    h->a_in_tmem = value != 0;
+  } else if (n == "unit_rows" && value > 0) {
+    h->unit_rows = value;
+  } else if (n == "max_ctas" && value >= 0) {
+    h->max_ctas = int(value);
+  } else {
+    return set_error(h, B200MS_EINVAL, "set_option: unknown option or bad value: " + n);
+  }
   return B200MS_OK;
 }
 

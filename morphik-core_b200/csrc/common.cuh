@@ -57,6 +57,7 @@ struct b200ms {
   int64_t launches = 0;
   int64_t unit_rows = 4096;
   int max_ctas = 0;
+  int a_in_tmem = 0;  // 1: feed the query operand of tcgen05.mma from TMEM (TS form), 0: from shared memory (SS form)
   CUtensorMap tmap_q;  // rebuilt per score call
 };
 

@@ -10,7 +10,8 @@
 // 32-row chunks by repeating the last row (min-Hamming invariant).  One warp owns one page; lane t owns query
 // token t of up to G resident 32-token groups (bits in registers).  Each 32-row chunk is fetched with ONE
 // coalesced 512-byte request (lane i loads row i as a uint4), parked in a per-warp shared-memory slab, and
-// replayed row by row as 128-bit broadcast reads; per (row, token) the work is 4 XOR + 4 POPC + 3 ADD + 1 MIN.
+// replayed row by row as 128-bit broadcast reads; per (row, token) the work is 6 LOP3 + 3 POPC (carry-save trick, see
+// the kernel) + 2 ADD + 1 MIN.
 // Bound: the integer POPC pipe, not HBM (16 B per patch vector) -- see DESIGN.md.
 #include "common.cuh"
 #include "ptx.cuh"
@@ -26,13 +27,19 @@ maxsim_b1_kernel(const uint4* __restrict__ rows, const int64_t* __restrict__ pag
                  int n_groups, int32_t* __restrict__ group_scores, int64_t ld) {
   __shared__ uint4 slab[kB1Warps][32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // Hamming of 128 bits with 3 POPC instead of 4 (the POPC pipe, 16 lanes/clk/SM, is the measured limiter):
+  // a carry-save adder compresses x0,x1,x2 (x_i = q_i ^ d_i) into sum s = x0^x1^x2 and carry c = maj(x0,x1,x2), so
+  //   ham = popc(x0)+popc(x1)+popc(x2)+popc(x3) = popc(s) + 2*popc(c) + popc(x3).
+  // s = (q0^q1^q2) ^ (d0^d1^d2): the query half is hoisted per token, the row half per row.
   uint4 q[G];
+  uint32_t qs[G];
   int ntok[G];
 #pragma unroll
   for (int g = 0; g < G; ++g) {
     const int gg = g_base + g;
     const bool live = gg < n_groups;
     q[g] = live ? __ldg(q_bits + int64_t(gg) * 32 + lane) : make_uint4(0, 0, 0, 0);
+    qs[g] = q[g].x ^ q[g].y ^ q[g].z;
     ntok[g] = live ? __ldg(group_ntok + gg) : 0;
   }
   const int64_t warp_global = int64_t(blockIdx.x) * kB1Warps + warp;
@@ -50,9 +57,12 @@ maxsim_b1_kernel(const uint4* __restrict__ rows, const int64_t* __restrict__ pag
 #pragma unroll 8
       for (int i = 0; i < 32; ++i) {
         const uint4 d = slab[warp][i];
+        const uint32_t ds = d.x ^ d.y ^ d.z;
 #pragma unroll
         for (int g = 0; g < G; ++g) {
-          const int ham = __popc(d.x ^ q[g].x) + __popc(d.y ^ q[g].y) + __popc(d.z ^ q[g].z) + __popc(d.w ^ q[g].w);
+          const uint32_t x0 = d.x ^ q[g].x, x1 = d.y ^ q[g].y, x2 = d.z ^ q[g].z;
+          const uint32_t c = (x0 & x1) | (x2 & (x0 | x1));  // majority: one LOP3
+          const int ham = __popc(ds ^ qs[g]) + 2 * __popc(c) + __popc(d.w ^ q[g].w);
           best[g] = min(best[g], ham);
         }
       }

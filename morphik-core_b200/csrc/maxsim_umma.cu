@@ -65,21 +65,30 @@ __device__ __forceinline__ Acc chunk_max(const uint32_t (&v)[32]) {
   return acc_max(a, b);
 }
 
-template <int KIND, int NM>
+// AT = false: A (queries) from shared memory, 4 accumulators of 128 columns          ("SS" form)
+// AT = true : A (queries) staged ONCE into TMEM columns [0, 64*NM) by tcgen05.st and fed from there ("TS" form), 4
+//             accumulators of 64 columns at [256, 512): the tensor core then reads only B from shared memory
+//             (64 B/clk instead of 128 B/clk at the nominal MMA rate) and the query tiles free 32 KB * NM of smem.
+template <int KIND, int NM, bool AT>
 __global__ void __launch_bounds__(kThreads, 1)
 maxsim_umma_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constant__ CUtensorMap tmap_q,
-                   const int32_t* __restrict__ chunk_page, const int32_t* __restrict__ unit_start, int n_units,
-                   int m_tile_base, int n_groups_real, typename Kind<KIND>::Acc* __restrict__ group_scores, int64_t ld,
-                   int num_stages) {
+                   const void* __restrict__ q_rows, int n_q_rows, const int32_t* __restrict__ chunk_page,
+                   const int32_t* __restrict__ unit_start, int n_units, int m_tile_base, int n_groups_real,
+                   typename Kind<KIND>::Acc* __restrict__ group_scores, int64_t ld, int num_stages) {
   using K = Kind<KIND>;
   using Acc = typename K::Acc;
   constexpr int NWG = NM == 1 ? 1 : 2;        // epilogue warpgroups in use
   constexpr int NMW = NM == 1 ? 1 : NM / 2;   // query tiles owned by one epilogue warpgroup
+  constexpr int kAccN = AT ? 64 : 128;        // columns (= patch rows) per accumulator
+  constexpr int kHalves = kTileN / kAccN;     // accumulators per (patch tile, query tile)
+  constexpr int kAccCol0 = AT ? 256 : 0;      // first accumulator column
+  constexpr int kQCols = KIND == 0 ? 64 : 32; // TMEM columns of one query tile (128 x 128 elements, 4 B per column)
+  constexpr int kKSteps = KIND == 0 ? 8 : 4;  // tcgen05.mma K steps per tile (32 B of K each)
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* smem_q = smem;                                   // NM query tiles
-  uint8_t* smem_st = smem + NM * K::kTileBytes;             // num_stages patch tiles
+  uint8_t* smem_q = smem;                                            // NM query tiles (SS form only)
+  uint8_t* smem_st = smem + (AT ? 0 : NM * K::kTileBytes);           // num_stages patch tiles
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_st + size_t(num_stages) * K::kTileBytes);
   uint64_t* full = bars;                     // [num_stages] TMA -> MMA
   uint64_t* empty = bars + 16;               // [num_stages] MMA -> TMA
@@ -93,7 +102,7 @@ maxsim_umma_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_c
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_rows);
-    prefetch_tmap(&tmap_q);
+    if (!AT) prefetch_tmap(&tmap_q);
     for (int i = 0; i < num_stages; ++i) {
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], 1);
@@ -102,7 +111,7 @@ maxsim_umma_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_c
       mbar_init(&tfull[i], 1);
       mbar_init(&tempty[i], 4);  // one arrive per epilogue warp of the owning warpgroup
     }
-    mbar_init(qfull, 1);
+    mbar_init(qfull, AT ? 4 : 1);
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc_512(tmem_slot);
@@ -114,15 +123,17 @@ maxsim_umma_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_c
   if (warp == 0) {
     // ================================================================ TMA producer
     if (lane == 0) {
-      const uint64_t pol_q = policy_evict_last();
       const uint64_t pol_rows = policy_evict_first();
-      mbar_expect_tx(qfull, NM * K::kTileBytes);
+      if constexpr (!AT) {
+        const uint64_t pol_q = policy_evict_last();
+        mbar_expect_tx(qfull, NM * K::kTileBytes);
 #pragma unroll
-      for (int m = 0; m < NM; ++m)
+        for (int m = 0; m < NM; ++m)
 #pragma unroll
-        for (int p = 0; p < K::kPanels; ++p)
-          tma_load_2d(&tmap_q, qfull, smem_q + m * K::kTileBytes + p * kSubtileBytes, p * K::kPanelElems,
-                      (m_tile_base + m) * kTileM, pol_q);
+          for (int p = 0; p < K::kPanels; ++p)
+            tma_load_2d(&tmap_q, qfull, smem_q + m * K::kTileBytes + p * kSubtileBytes, p * K::kPanelElems,
+                        (m_tile_base + m) * kTileM, pol_q);
+      }
       int stage = 0;
       uint32_t phase = 0;
       for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
@@ -147,7 +158,7 @@ maxsim_umma_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_c
     // ================================================================ MMA issuer
     // The whole warp walks the loop (so every address/descriptor is warp-uniform and lives in uniform registers);
     // only the tcgen05.mma / tcgen05.commit themselves are issued by the lane elect.sync picks.
-    constexpr uint32_t idesc = umma_idesc(KIND, kTileM, kTileN);
+    constexpr uint32_t idesc = umma_idesc(KIND, kTileM, kAccN);
     constexpr uint32_t kTileDesc = K::kTileBytes >> 4;  // tile size in descriptor units (16 B)
     mbar_wait(qfull, 0);
     tc_fence_after();
@@ -164,24 +175,34 @@ maxsim_umma_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_c
         tc_fence_after();
         const uint64_t bd = b_desc0 + uint64_t(uint32_t(stage) * kTileDesc);
 #pragma unroll 1
-        for (int m = 0; m < NM; ++m, ++seq) {
-          const uint32_t buf = seq & (kNumAccum - 1);
-          mbar_wait(&tempty[buf], ((seq >> 2) & 1) ^ 1);
-          tc_fence_after();
-          if (elect_one()) {
-            const uint32_t d_tmem = tmem_base + buf * kTileN;
-            const uint64_t ad = a_desc0 + uint64_t(uint32_t(m) * kTileDesc);
+        for (int m = 0; m < NM; ++m) {
 #pragma unroll
-            for (int p = 0; p < K::kPanels; ++p) {
+          for (int hf = 0; hf < kHalves; ++hf, ++seq) {
+            const uint32_t buf = seq & (kNumAccum - 1);
+            mbar_wait(&tempty[buf], ((seq >> 2) & 1) ^ 1);
+            tc_fence_after();
+            if (elect_one()) {
+              const uint32_t d_tmem = tmem_base + kAccCol0 + buf * kAccN;
+              if constexpr (AT) {
+                const uint32_t a_tmem = tmem_base + uint32_t(m) * kQCols;
+                const uint64_t bh = bd + uint64_t((hf * kAccN * 128) >> 4);  // rows hf*64.. of every 128 B panel
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {  // 4 x 32 B of K per 128 B panel; +2 descriptor units per step
-                const uint32_t off = (p * kSubtileBytes + k * 32) >> 4;
-                umma_ss<KIND>(d_tmem, ad + off, bd + off, idesc, (p | k) != 0);
+                for (int ks = 0; ks < kKSteps; ++ks) {
+                  const uint32_t off = ((ks >> 2) * kSubtileBytes + (ks & 3) * 32) >> 4;
+                  umma_ts<KIND>(d_tmem, a_tmem + ks * 8, bh + off, idesc, ks != 0);
+                }
+              } else {
+                const uint64_t ad = a_desc0 + uint64_t(uint32_t(m) * kTileDesc);
+#pragma unroll
+                for (int ks = 0; ks < kKSteps; ++ks) {  // 32 B of K per step; 4 steps per 128 B panel
+                  const uint32_t off = ((ks >> 2) * kSubtileBytes + (ks & 3) * 32) >> 4;
+                  umma_ss<KIND>(d_tmem, ad + off, bd + off, idesc, ks != 0);
+                }
               }
+              umma_commit(&tfull[buf]);
             }
-            umma_commit(&tfull[buf]);
+            __syncwarp();
           }
-          __syncwarp();
         }
         if (elect_one()) umma_commit(&empty[stage]);  // stage reusable once every query tile has consumed it
         __syncwarp();
@@ -194,12 +215,44 @@ maxsim_umma_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_c
   } else if (warp >= 4) {
     // ================================================================ epilogue warpgroups
     const int wg = (warp - 4) >> 2;
-    const int quad = warp & 3;  // TMEM lane quadrant this warp may read
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    const uint32_t lane_base = tmem_base + (uint32_t(quad * 32) << 16);
+
+    if constexpr (AT) {
+      // Stage the query tiles into TMEM once: thread (quad, lane) owns token row quad*32+lane of every tile and writes its
+      // 256 B (bf16) / 128 B (s8) as consecutive 32-bit columns -- the K-major A layout tcgen05.mma reads from TMEM.
+      if (wg == 0) {
+        const int row_in_tile = quad * 32 + lane;
+#pragma unroll 1
+        for (int m = 0; m < NM; ++m) {
+          const int64_t row = int64_t(m_tile_base + m) * kTileM + row_in_tile;
+          const bool live = row < n_q_rows;
+#pragma unroll
+          for (int c = 0; c < kQCols; c += 32) {
+            uint32_t v[32];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              uint4 w = make_uint4(0, 0, 0, 0);
+              if (live) w = __ldg(reinterpret_cast<const uint4*>(static_cast<const uint8_t*>(q_rows) + row * (kQCols * 4)) + (c >> 2) + j);
+              v[4 * j] = w.x;
+              v[4 * j + 1] = w.y;
+              v[4 * j + 2] = w.z;
+              v[4 * j + 3] = w.w;
+            }
+            tmem_st_32x32(lane_base + m * kQCols + c, v);
+          }
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(qfull);
+      }
+    }
+
     if (wg < NWG) {
       Acc runmax[NMW];
       int cur_page[NMW];
       uint32_t tile_seq = 0;
-      const uint32_t lane_base = tmem_base + (uint32_t(quad * 32) << 16);
 
       for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
         const int c0 = __ldg(unit_start + u), c1 = __ldg(unit_start + u + 1);
@@ -218,9 +271,9 @@ maxsim_umma_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_c
 #pragma unroll 1
           for (int i = 0; i < NMW; ++i) {
             const int m = NM == 1 ? 0 : (2 * i + wg);
-            const uint32_t seq = tile_seq * NM + m;
-            const uint32_t buf = seq & (kNumAccum - 1);
+            const uint32_t seq0 = (tile_seq * NM + m) * kHalves;
             const int group = (m_tile_base + m) * 4 + quad;
+            const bool active = group < n_groups_real;
             Acc rm = Acc(0);
             int cp = -1;
 #pragma unroll
@@ -229,25 +282,38 @@ maxsim_umma_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_c
                 rm = runmax[j];
                 cp = cur_page[j];
               }
-            mbar_wait(&tfull[buf], (seq >> 2) & 1);
-            tc_fence_after();
-            if (group < n_groups_real) {
-              const uint32_t taddr = lane_base + buf * kTileN;
-              uint32_t va[32], vb[32];
-              Acc cm[4];
-              tmem_ld_32x32(taddr, va);
-              tmem_ld_32x32(taddr + 32, vb);
-              tmem_ld_wait();
-              cm[0] = chunk_max<Acc>(va);
-              cm[1] = chunk_max<Acc>(vb);
-              tmem_ld_32x32(taddr + 64, va);
-              tmem_ld_32x32(taddr + 96, vb);
-              tmem_ld_wait();
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(&tempty[buf]);  // accumulator drained: MMA may overwrite it
-              cm[2] = chunk_max<Acc>(va);
-              cm[3] = chunk_max<Acc>(vb);
+            Acc cm[4];
+#pragma unroll
+            for (int hf = 0; hf < kHalves; ++hf) {
+              const uint32_t seq = seq0 + hf;
+              const uint32_t buf = seq & (kNumAccum - 1);
+              mbar_wait(&tfull[buf], (seq >> 2) & 1);
+              tc_fence_after();
+              if (active) {
+                const uint32_t taddr = lane_base + kAccCol0 + buf * kAccN;
+                uint32_t va[32], vb[32];
+                tmem_ld_32x32(taddr, va);
+                tmem_ld_32x32(taddr + 32, vb);
+                tmem_ld_wait();
+                if constexpr (kHalves == 1) {
+                  cm[0] = chunk_max<Acc>(va);
+                  cm[1] = chunk_max<Acc>(vb);
+                  tmem_ld_32x32(taddr + 64, va);
+                  tmem_ld_32x32(taddr + 96, vb);
+                  tmem_ld_wait();
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[buf]);  // accumulator drained: MMA may overwrite it
+                cm[kHalves == 1 ? 2 : 2 * hf] = chunk_max<Acc>(va);
+                cm[kHalves == 1 ? 3 : 2 * hf + 1] = chunk_max<Acc>(vb);
+              } else {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[buf]);
+              }
+            }
+            if (active) {
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 if (pg[j] < 0) continue;  // chunk belongs to the next unit
@@ -262,10 +328,6 @@ maxsim_umma_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_c
                   rm = acc_max(rm, cm[j]);
                 }
               }
-            } else {
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(&tempty[buf]);
             }
 #pragma unroll
             for (int j = 0; j < NMW; ++j)
@@ -298,47 +360,50 @@ maxsim_umma_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_c
 }
 
 // ---------------------------------------------------------------------------------------------- host side
-template <int KIND, int NM>
-static int launch_one(b200ms_t* h, const CUtensorMap& tq, int m_tile_base, int n_groups_real, void* scores,
-                      int64_t ld, cudaStream_t s) {
+template <int KIND, int NM, bool AT>
+static int launch_one(b200ms_t* h, const CUtensorMap& tq, const void* q_rows, int n_q_rows, int m_tile_base,
+                      int n_groups_real, void* scores, int64_t ld, cudaStream_t s) {
   using K = Kind<KIND>;
   const Corpus& c = h->corpus;
-  const uint32_t avail = kSmemLimit - 1024 /*align*/ - kBarrierBytes - NM * K::kTileBytes;
+  const uint32_t q_bytes = AT ? 0 : NM * K::kTileBytes;
+  const uint32_t avail = kSmemLimit - 1024 /*align*/ - kBarrierBytes - q_bytes;
   int stages = int(avail / K::kTileBytes);
   if (stages > 8) stages = 8;
   if (stages < 2) return set_error(h, B200MS_EINVAL, "maxsim_umma: not enough shared memory for 2 stages");
-  const uint32_t smem = 1024 + NM * K::kTileBytes + uint32_t(stages) * K::kTileBytes + kBarrierBytes;
-  auto kern = maxsim_umma_kernel<KIND, NM>;
+  const uint32_t smem = 1024 + q_bytes + uint32_t(stages) * K::kTileBytes + kBarrierBytes;
+  auto kern = maxsim_umma_kernel<KIND, NM, AT>;
   if (int e = check_cuda(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)),
                          "cudaFuncSetAttribute(maxsim_umma)"))
     return e;
   int grid = h->max_ctas > 0 ? h->max_ctas : h->num_sms;
   if (grid > c.n_units) grid = c.n_units;
   if (grid < 1) return B200MS_OK;
-  kern<<<grid, kThreads, smem, s>>>(c.tmap, tq, static_cast<const int32_t*>(h->chunk_page.p),
+  kern<<<grid, kThreads, smem, s>>>(c.tmap, tq, q_rows, n_q_rows, static_cast<const int32_t*>(h->chunk_page.p),
                                    static_cast<const int32_t*>(h->unit_start.p), c.n_units, m_tile_base, n_groups_real,
                                    static_cast<typename K::Acc*>(scores), ld, stages);
   h->launches++;
   return check_cuda(h, cudaGetLastError(), "launch maxsim_umma");
 }
 
-template <int KIND>
-static int launch_kind(b200ms_t* h, const CUtensorMap& tq, int n_groups_real, int n_mtiles, void* scores, int64_t ld,
-                       cudaStream_t s) {
+template <int KIND, bool AT>
+static int launch_kind(b200ms_t* h, const CUtensorMap& tq, const void* q_rows, int n_q_rows, int n_groups_real,
+                       int n_mtiles, void* scores, int64_t ld, cudaStream_t s) {
+  // resident query tiles per pass: SS form is bounded by shared memory (bf16 4, s8 8), TS form by the 256 TMEM columns
+  // left of the accumulators (bf16 4 x 64 columns, s8 8 x 32 columns)
   constexpr int kMaxNM = KIND == 0 ? 4 : 8;
   int base = 0;
   while (base < n_mtiles) {
     const int rem = n_mtiles - base;
     int nm = 1;
-    while (nm < rem && nm < kMaxNM) nm <<= 1;  // round up: a phantom (all-zero, TMA OOB-filled) tile beats a 2nd pass
+    while (nm < rem && nm < kMaxNM) nm <<= 1;  // round up: a phantom (all-zero) tile beats a 2nd pass over the corpus
     int e;
     switch (nm) {
-      case 1: e = launch_one<KIND, 1>(h, tq, base, n_groups_real, scores, ld, s); break;
-      case 2: e = launch_one<KIND, 2>(h, tq, base, n_groups_real, scores, ld, s); break;
-      case 4: e = launch_one<KIND, 4>(h, tq, base, n_groups_real, scores, ld, s); break;
+      case 1: e = launch_one<KIND, 1, AT>(h, tq, q_rows, n_q_rows, base, n_groups_real, scores, ld, s); break;
+      case 2: e = launch_one<KIND, 2, AT>(h, tq, q_rows, n_q_rows, base, n_groups_real, scores, ld, s); break;
+      case 4: e = launch_one<KIND, 4, AT>(h, tq, q_rows, n_q_rows, base, n_groups_real, scores, ld, s); break;
       default:
         if constexpr (KIND == 1) {
-          e = launch_one<KIND, 8>(h, tq, base, n_groups_real, scores, ld, s);
+          e = launch_one<KIND, 8, AT>(h, tq, q_rows, n_q_rows, base, n_groups_real, scores, ld, s);
         } else {
           e = set_error(h, B200MS_EINVAL, "maxsim_umma: bad NM");
         }
@@ -355,9 +420,16 @@ int launch_score_umma(b200ms_t* h, const void* q_packed, int n_groups_real, void
   if (!c.has_tmap) return set_error(h, B200MS_ESTATE, "score: corpus has no TMA descriptor");
   const int n_groups_padded = (n_groups_real + 3) & ~3;
   const int n_mtiles = n_groups_padded / 4;
-  if (int e = make_tmap_rows(h, &h->tmap_q, q_packed, c.dtype, int64_t(n_groups_padded) * kGroup, kTileM)) return e;
-  if (c.dtype == B200MS_BF16) return launch_kind<0>(h, h->tmap_q, n_groups_real, n_mtiles, group_scores, ld, s);
-  return launch_kind<1>(h, h->tmap_q, n_groups_real, n_mtiles, group_scores, ld, s);
+  const int n_q_rows = n_groups_padded * kGroup;
+  const bool ts = h->a_in_tmem != 0;
+  if (!ts)
+    if (int e = make_tmap_rows(h, &h->tmap_q, q_packed, c.dtype, int64_t(n_q_rows), kTileM)) return e;
+  if (c.dtype == B200MS_BF16) {
+    return ts ? launch_kind<0, true>(h, h->tmap_q, q_packed, n_q_rows, n_groups_real, n_mtiles, group_scores, ld, s)
+              : launch_kind<0, false>(h, h->tmap_q, q_packed, n_q_rows, n_groups_real, n_mtiles, group_scores, ld, s);
+  }
+  return ts ? launch_kind<1, true>(h, h->tmap_q, q_packed, n_q_rows, n_groups_real, n_mtiles, group_scores, ld, s)
+            : launch_kind<1, false>(h, h->tmap_q, q_packed, n_q_rows, n_groups_real, n_mtiles, group_scores, ld, s);
 }
 
 }  // namespace bms

@@ -103,6 +103,11 @@ class MaxSimIndex:
         self.h.check(nat.lib.b200ms_set_tuning(self.h.ptr, int(unit_rows), int(max_ctas)), "b200ms_set_tuning")
         self._attached = False
 
+    def set_option(self, name: str, value: int):
+        self.h.check(nat.lib.b200ms_set_option(self.h.ptr, name.encode(), int(value)), f"b200ms_set_option({name})")
+        if name == "unit_rows":
+            self._attached = False
+
     def _stream(self):
         return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
