@@ -140,6 +140,32 @@ int b200ms_search_device(b200ms_t* h, const void* q_dev, int src_dtype, const in
                          const uint32_t* allow_mask_dev, float i8_q_scale, float score_scale, int64_t id_base,
                          float* top_scores_dev, int64_t* top_ids_dev, int32_t* top_counts_dev, void* stream);
 
+/* MaxSim over an explicit candidate list (the "rerank" half of a two-stage search, fast_multivector_store.py:545-557):
+ * cand_ids_dev = device array of n_cand page ids (-1 = unused slot).  Only those pages are scanned; ties break towards
+ * the earlier candidate slot (= better first-stage rank).  Outputs as b200ms_search_device. */
+int b200ms_rerank_device(b200ms_t* h, const void* q_dev, int src_dtype, const int32_t* q_lens, int n_q,
+                         const int64_t* cand_ids_dev, int n_cand, int k, float i8_q_scale, float score_scale,
+                         float* top_scores_dev, int64_t* top_ids_dev, int32_t* top_counts_dev, void* stream);
+
+/* ---- fixed-dimensional encodings (MUVERA FDE): candidate generation in front of the scorer ---------------------------
+ * Replaces the `fixed_dimensional_encoding` C++ extension (fast_multivector_store.py:325-331,447-449,521) and the
+ * Turbopuffer ANN over its output (:526-532) with an exact encoder and an exhaustive cosine scan.
+ * configure: reps repetitions x 2^ksim SimHash partitions x proj_dim AMS-sketch dims = fde_dim floats per item.
+ *   simhash [reps,128,ksim] Gaussian, ams_index [reps,128] in [0,proj_dim), ams_sign [reps,128] = +-1 (HOST arrays).
+ * encode: items stored back to back at rows (device F32|BF16, [sum len,128]); is_document 0: SUM per partition (query),
+ *   1: AVERAGE per partition, empty partition -> 0 (document); out device float32 [n_items, fde_dim].
+ * finalize: fp32 FDEs -> bf16 rows of the FDE corpus + 1/||row||.
+ * scan: scores[q,p] = <q_fde[q], F[p]> * inv_norm[p]  (cosine ranking);  feed to b200ms_topk (score dtype F32,
+ *   group_offsets = 0..n_q) to get the candidate list. */
+int b200ms_fde_configure(b200ms_t* h, int reps, int ksim, int proj_dim, float scale, const float* simhash,
+                         const int32_t* ams_index, const float* ams_sign);
+int64_t b200ms_fde_dim(const b200ms_t* h);
+int b200ms_fde_encode(b200ms_t* h, const void* rows, int src_dtype, const int32_t* item_lens, int64_t n_items,
+                      int is_document, float* out, void* stream);
+int b200ms_fde_finalize(b200ms_t* h, const float* fde, int64_t n, void* out_rows, float* inv_norm, void* stream);
+int b200ms_fde_scan(b200ms_t* h, const void* fde_rows, const float* inv_norm, int64_t n_pages, const float* q_fde, int n_q,
+                    float* scores, int64_t ld, void* stream);
+
 /* ---- instrumentation ------------------------------------------------------------------------- */
 /* Kernels launched by this handle since creation (bench.py's gpu_launches claim). */
 int64_t b200ms_launch_count(const b200ms_t* h);

@@ -58,6 +58,12 @@ def _load() -> ctypes.CDLL:
         "b200ms_last_score_ms": (c_float, [vp]),
         "b200ms_set_tuning": (c_int, [vp, c_int64, c_int]),
         "b200ms_set_option": (c_int, [vp, c_char_p, c_int64]),
+        "b200ms_rerank_device": (c_int, [vp, vp, c_int, i32p, c_int, vp, c_int, c_int, c_float, c_float, vp, vp, vp, vp]),
+        "b200ms_fde_configure": (c_int, [vp, c_int, c_int, c_int, c_float, vp, vp, vp]),
+        "b200ms_fde_dim": (c_int64, [vp]),
+        "b200ms_fde_encode": (c_int, [vp, vp, c_int, i32p, c_int64, c_int, vp, vp]),
+        "b200ms_fde_finalize": (c_int, [vp, vp, c_int64, vp, vp, vp]),
+        "b200ms_fde_scan": (c_int, [vp, vp, vp, c_int64, vp, c_int, vp, c_int64, vp]),
         "b200ms_score_call_count": (c_int64, [vp]),
         "b200ms_score_times_ms": (c_int, [vp, f32p, c_int]),
     }
@@ -75,7 +81,8 @@ EXPORTED = [
     "b200ms_pack_pages", "b200ms_set_corpus", "b200ms_corpus_pages", "b200ms_corpus_rows", "b200ms_pack_queries",
     "b200ms_score", "b200ms_topk", "b200ms_merge_topk", "b200ms_search_host", "b200ms_search_device",
     "b200ms_launch_count", "b200ms_last_score_ms", "b200ms_set_tuning", "b200ms_score_call_count",
-    "b200ms_score_times_ms", "b200ms_set_option",
+    "b200ms_score_times_ms", "b200ms_set_option", "b200ms_rerank_device", "b200ms_fde_configure", "b200ms_fde_dim",
+    "b200ms_fde_encode", "b200ms_fde_finalize", "b200ms_fde_scan",
 ]
 
 

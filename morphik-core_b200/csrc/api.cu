@@ -165,7 +165,8 @@ B200MS_API int b200ms_destroy(b200ms_t* h) {
   DeviceGuard g(h->device);
   cudaDeviceSynchronize();
   DeviceBuf* bufs[] = {&h->chunk_page, &h->unit_start, &h->page_start, &h->meta_a, &h->meta_b, &h->meta_c, &h->q_raw,
-                       &h->q_packed, &h->scores, &h->mask, &h->out_s, &h->out_i, &h->out_c};
+                       &h->q_packed, &h->scores, &h->mask, &h->out_s, &h->out_i, &h->out_c, &h->cand_start, &h->cand_end,
+                       &h->cand_mask, &h->fde_simhash, &h->fde_ams_index, &h->fde_ams_sign, &h->fde_tmp};
   for (DeviceBuf* b : bufs)
     if (b->p) cudaFree(b->p);
   if (h->pinned) cudaFreeHost(h->pinned);
@@ -350,13 +351,17 @@ B200MS_API int b200ms_set_corpus(b200ms_t* h, const void* rows, int dtype, const
 }
 
 // ------------------------------------------------------------------------------------------------ hot path
+// cand_ids == NULL: scan the whole corpus, scores indexed by page id.  Otherwise: score only the n_cand candidate pages
+// (device array of page ids, -1 = unused slot), scores indexed by candidate slot.
 static int score_impl(b200ms_t* h, const void* q_packed, int n_groups, const int32_t* q_lens,
-                      const int32_t* group_offsets, int n_q, void* group_scores, int64_t ld, cudaStream_t s) {
+                      const int32_t* group_offsets, int n_q, void* group_scores, int64_t ld, const int64_t* cand_ids,
+                      int n_cand, cudaStream_t s) {
   const Corpus& c = h->corpus;
   if (c.dtype < 0) return set_error(h, B200MS_ESTATE, "score: no corpus attached (call b200ms_set_corpus first)");
-  if (n_groups < 0 || ld < c.n_pages || (n_groups > 0 && (!q_packed || !group_scores)))
+  const int64_t n_items = cand_ids ? n_cand : c.n_pages;
+  if (n_groups < 0 || ld < n_items || n_cand < 0 || (n_groups > 0 && (!q_packed || !group_scores)))
     return set_error(h, B200MS_EINVAL, "score: bad arguments");
-  if (n_groups == 0 || c.n_pages == 0) return B200MS_OK;
+  if (n_groups == 0 || n_items == 0 || c.n_pages == 0) return B200MS_OK;
   const int slot = int(h->ev_count % b200ms::kEvRing);
   const int n_groups_padded = (n_groups + 3) & ~3;
   if (c.dtype == B200MS_B1) {
@@ -371,18 +376,32 @@ static int score_impl(b200ms_t* h, const void* q_packed, int n_groups, const int
     }
     if (int e = upload(h, h->meta_c, ntok.data(), ntok.size() * 4, s)) return e;
     cudaEventRecord(h->ev0[slot], s);
-    if (int e = launch_score_b1(h, q_packed, n_groups, static_cast<const int32_t*>(h->meta_c.p), group_scores, ld, s)) return e;
+    if (int e = launch_score_b1(h, cand_ids, n_cand, q_packed, n_groups, static_cast<const int32_t*>(h->meta_c.p),
+                                group_scores, ld, s))
+      return e;
     cudaEventRecord(h->ev1[slot], s);
     h->ev_count++;
     // ntok is pageable host memory: the async upload staged it before returning, nothing else to wait for
     return B200MS_OK;
   }
-  // pages with zero rows are never touched by the tile kernel: they score 0 (COALESCE(..., 0.0))
-  if (c.has_empty) {
+  // pages with zero rows (and unused candidate slots) are never touched by the tile kernel: they score 0
+  if (c.has_empty || cand_ids) {
     if (int e = check_cuda(h, cudaMemsetAsync(group_scores, 0, size_t(n_groups_padded) * size_t(ld) * 4, s), "score: memset")) return e;
   }
+  UnitPlan plan;
+  if (cand_ids) {
+    if (int e = reserve(h, h->cand_start, size_t(n_cand) * 4)) return e;
+    if (int e = reserve(h, h->cand_end, size_t(n_cand) * 4)) return e;
+    if (int e = launch_cand_units(h, cand_ids, n_cand, static_cast<int32_t*>(h->cand_start.p),
+                                  static_cast<int32_t*>(h->cand_end.p), nullptr, s))
+      return e;
+    plan.start = static_cast<const int32_t*>(h->cand_start.p);
+    plan.end = static_cast<const int32_t*>(h->cand_end.p);
+    plan.n_units = n_cand;
+    plan.slot_mode = 1;
+  }
   cudaEventRecord(h->ev0[slot], s);
-  if (int e = launch_score_umma(h, q_packed, n_groups, group_scores, ld, s)) return e;
+  if (int e = launch_score_umma(h, cand_ids ? &plan : nullptr, q_packed, n_groups, group_scores, ld, s)) return e;
   cudaEventRecord(h->ev1[slot], s);
   h->ev_count++;
   return B200MS_OK;
@@ -392,7 +411,7 @@ B200MS_API int b200ms_score(b200ms_t* h, const void* q_packed, int n_groups, con
                             const int32_t* group_offsets, int n_q, void* group_scores, int64_t ld, void* stream) {
   if (!h) return B200MS_EINVAL;
   DeviceGuard g(h->device);
-  return score_impl(h, q_packed, n_groups, q_lens, group_offsets, n_q, group_scores, ld, static_cast<cudaStream_t>(stream));
+  return score_impl(h, q_packed, n_groups, q_lens, group_offsets, n_q, group_scores, ld, nullptr, 0, static_cast<cudaStream_t>(stream));
 }
 
 static int score_time_of(b200ms_t* h, int64_t idx, float* ms) {
@@ -435,7 +454,7 @@ B200MS_API int b200ms_topk(b200ms_t* h, const void* group_scores, int score_dtyp
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (int e = upload(h, h->meta_a, group_offsets, size_t(n_q + 1) * 4, s)) return e;
   return launch_topk(h, group_scores, score_dtype, n_pages, ld, static_cast<const int32_t*>(h->meta_a.p), n_q, allow_mask,
-                     k, scale, id_base, top_scores, top_ids, top_counts, s);
+                     k, scale, id_base, nullptr, top_scores, top_ids, top_counts, s);
 }
 
 B200MS_API int b200ms_merge_topk(b200ms_t* h, const float* cand_scores, const int64_t* cand_ids, int n_q, int m, int k,
@@ -451,26 +470,44 @@ B200MS_API int b200ms_merge_topk(b200ms_t* h, const float* cand_scores, const in
 
 static int search_impl(b200ms_t* h, const void* q_dev, int src_dtype, const int32_t* q_lens, int n_q, int k,
                        const uint32_t* allow_dev, float i8_q_scale, float score_scale, int64_t id_base, float* ts,
-                       int64_t* ti, int32_t* tc, cudaStream_t s) {
+                       int64_t* ti, int32_t* tc, cudaStream_t s, const int64_t* cand_ids = nullptr, int n_cand = 0) {
   const Corpus& c = h->corpus;
   if (c.dtype < 0) return set_error(h, B200MS_ESTATE, "search: no corpus attached (call b200ms_set_corpus first)");
   if (n_q < 1 || !q_lens || !q_dev || k < 1 || k > B200MS_MAX_K || !ts || !ti || !tc)
     return set_error(h, B200MS_EINVAL, "search: bad arguments (n_q >= 1, 1 <= k <= 4096)");
   const int64_t groups = b200ms_query_groups(q_lens, n_q);
   const int64_t groups_padded = (groups + 3) & ~int64_t(3);
-  const int64_t ld = (c.n_pages + 31) & ~int64_t(31);
+  const int64_t n_items = cand_ids ? n_cand : c.n_pages;
+  const int64_t ld = (n_items + 31) & ~int64_t(31);
   if (int e = reserve(h, h->q_packed, size_t(groups_padded > 0 ? groups_padded : 4) * kGroup * size_t(b200ms_row_bytes(c.dtype)))) return e;
   if (int e = reserve(h, h->scores, size_t(groups_padded > 0 ? groups_padded : 4) * size_t(ld > 0 ? ld : 32) * 4)) return e;
   std::vector<int32_t> goff(size_t(n_q) + 1);
   int ng = 0;
   if (int e = b200ms_pack_queries(h, q_dev, src_dtype, q_lens, n_q, h->q_packed.p, c.dtype, i8_q_scale, goff.data(), &ng, s)) return e;
-  if (int e = score_impl(h, h->q_packed.p, ng, q_lens, goff.data(), n_q, h->scores.p, ld, s)) return e;
-  if (ng == 0 || c.n_pages == 0) {
+  if (int e = score_impl(h, h->q_packed.p, ng, q_lens, goff.data(), n_q, h->scores.p, ld, cand_ids, n_cand, s)) return e;
+  if (ng == 0 || n_items == 0) {
     // nothing scored: every page (if any) has score 0 -- still a defined ranking
     if (int e = check_cuda(h, cudaMemsetAsync(h->scores.p, 0, size_t(groups_padded > 0 ? groups_padded : 4) * size_t(ld > 0 ? ld : 32) * 4, s), "search: memset")) return e;
   }
   const int sdt = c.dtype == B200MS_BF16 ? B200MS_F32 : B200MS_I32;
-  return b200ms_topk(h, h->scores.p, sdt, c.n_pages, ld, goff.data(), n_q, allow_dev, k, score_scale, id_base, ts, ti, tc, s);
+  if (!cand_ids) return b200ms_topk(h, h->scores.p, sdt, c.n_pages, ld, goff.data(), n_q, allow_dev, k, score_scale, id_base, ts, ti, tc, s);
+  // candidate mode: rank the slots (ties -> lower slot = better first-stage rank), report the page ids; unused slots masked
+  if (int e = reserve(h, h->cand_mask, size_t((n_cand + 31) / 32) * 4)) return e;
+  if (int e = launch_cand_units(h, cand_ids, n_cand, nullptr, nullptr, static_cast<uint32_t*>(h->cand_mask.p), s)) return e;
+  if (int e = upload(h, h->meta_a, goff.data(), size_t(n_q + 1) * 4, s)) return e;
+  return launch_topk(h, h->scores.p, sdt, n_cand, ld, static_cast<const int32_t*>(h->meta_a.p), n_q,
+                     static_cast<const uint32_t*>(h->cand_mask.p), k, score_scale, 0, cand_ids, ts, ti, tc, s);
+}
+
+B200MS_API int b200ms_rerank_device(b200ms_t* h, const void* q_dev, int src_dtype, const int32_t* q_lens, int n_q,
+                                    const int64_t* cand_ids_dev, int n_cand, int k, float i8_q_scale, float score_scale,
+                                    float* top_scores_dev, int64_t* top_ids_dev, int32_t* top_counts_dev, void* stream) {
+  if (!h) return B200MS_EINVAL;
+  if (!src_dtype_ok(src_dtype) || !cand_ids_dev || n_cand < 1)
+    return set_error(h, B200MS_EINVAL, "rerank_device: bad arguments (F32/BF16 queries, n_cand >= 1)");
+  DeviceGuard g(h->device);
+  return search_impl(h, q_dev, src_dtype, q_lens, n_q, k, nullptr, i8_q_scale, score_scale, 0, top_scores_dev, top_ids_dev,
+                     top_counts_dev, static_cast<cudaStream_t>(stream), cand_ids_dev, n_cand);
 }
 
 B200MS_API int b200ms_search_device(b200ms_t* h, const void* q_dev, int src_dtype, const int32_t* q_lens, int n_q, int k,
@@ -512,4 +549,64 @@ B200MS_API int b200ms_search_host(b200ms_t* h, const float* q_host, const int32_
   cudaMemcpyAsync(top_ids_host, h->out_i.p, size_t(n_q) * k * 8, cudaMemcpyDeviceToHost, s);
   cudaMemcpyAsync(top_counts_host, h->out_c.p, size_t(n_q) * 4, cudaMemcpyDeviceToHost, s);
   return check_cuda(h, cudaStreamSynchronize(s), "search_host: stream sync");
+}
+
+// ------------------------------------------------------------------------------------------------ FDE (next row f-1)
+B200MS_API int b200ms_fde_configure(b200ms_t* h, int reps, int ksim, int proj_dim, float scale, const float* simhash,
+                                    const int32_t* ams_index, const float* ams_sign) {
+  if (!h) return B200MS_EINVAL;
+  if (reps < 1 || ksim < 1 || ksim > 8 || proj_dim < 1 || proj_dim > 64 || (proj_dim << ksim) > 512 || ((proj_dim << ksim) % 8) ||
+      !simhash || !ams_index || !ams_sign)
+    return set_error(h, B200MS_EINVAL, "fde_configure: need 1<=ksim<=8, proj_dim<=64, proj_dim*2^ksim <= 512 and a multiple of 8");
+  for (int i = 0; i < reps * kDim; ++i)
+    if (ams_index[i] < 0 || ams_index[i] >= proj_dim) return set_error(h, B200MS_EINVAL, "fde_configure: ams_index out of range");
+  DeviceGuard g(h->device);
+  cudaStream_t s = h->stream;
+  if (int e = upload(h, h->fde_simhash, simhash, size_t(reps) * kDim * ksim * 4, s)) return e;
+  if (int e = upload(h, h->fde_ams_index, ams_index, size_t(reps) * kDim * 4, s)) return e;
+  if (int e = upload(h, h->fde_ams_sign, ams_sign, size_t(reps) * kDim * 4, s)) return e;
+  if (int e = check_cuda(h, cudaStreamSynchronize(s), "fde_configure: sync")) return e;
+  h->fde_reps = reps;
+  h->fde_ksim = ksim;
+  h->fde_proj = proj_dim;
+  h->fde_scale = scale;
+  h->fde_dim = reps * (1 << ksim) * proj_dim;
+  return B200MS_OK;
+}
+
+B200MS_API int64_t b200ms_fde_dim(const b200ms_t* h) { return h ? h->fde_dim : 0; }
+
+B200MS_API int b200ms_fde_encode(b200ms_t* h, const void* rows, int src_dtype, const int32_t* item_lens, int64_t n_items,
+                                 int is_document, float* out, void* stream) {
+  if (!h) return B200MS_EINVAL;
+  if (h->fde_dim == 0) return set_error(h, B200MS_ESTATE, "fde_encode: call b200ms_fde_configure first");
+  if (!src_dtype_ok(src_dtype) || n_items < 0 || n_items > 65535 || (n_items > 0 && (!rows || !item_lens || !out)))
+    return set_error(h, B200MS_EINVAL, "fde_encode: bad arguments (at most 65535 items per call)");
+  if (n_items == 0) return B200MS_OK;
+  DeviceGuard g(h->device);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  std::vector<int64_t> st(size_t(n_items) + 1);
+  st[0] = 0;
+  for (int64_t i = 0; i < n_items; ++i) st[i + 1] = st[i] + (item_lens[i] > 0 ? item_lens[i] : 0);
+  if (int e = upload(h, h->meta_a, st.data(), st.size() * 8, s)) return e;
+  return launch_fde_encode(h, rows, src_dtype, static_cast<const int64_t*>(h->meta_a.p), int(n_items), is_document, out, s);
+}
+
+B200MS_API int b200ms_fde_finalize(b200ms_t* h, const float* fde, int64_t n, void* out_rows, float* inv_norm, void* stream) {
+  if (!h) return B200MS_EINVAL;
+  if (h->fde_dim == 0) return set_error(h, B200MS_ESTATE, "fde_finalize: call b200ms_fde_configure first");
+  if (n < 0 || (n > 0 && (!fde || !out_rows || !inv_norm))) return set_error(h, B200MS_EINVAL, "fde_finalize: bad arguments");
+  DeviceGuard g(h->device);
+  return launch_fde_finalize(h, fde, n, out_rows, inv_norm, static_cast<cudaStream_t>(stream));
+}
+
+B200MS_API int b200ms_fde_scan(b200ms_t* h, const void* fde_rows, const float* inv_norm, int64_t n_pages, const float* q_fde,
+                               int n_q, float* scores, int64_t ld, void* stream) {
+  if (!h) return B200MS_EINVAL;
+  if (h->fde_dim == 0) return set_error(h, B200MS_ESTATE, "fde_scan: call b200ms_fde_configure first");
+  if (n_pages < 0 || n_q < 0 || ld < n_pages || (n_pages > 0 && n_q > 0 && (!fde_rows || !inv_norm || !q_fde || !scores)) ||
+      (reinterpret_cast<uintptr_t>(fde_rows) & 15))
+    return set_error(h, B200MS_EINVAL, "fde_scan: bad arguments (rows 16-byte aligned, ld >= n_pages)");
+  DeviceGuard g(h->device);
+  return launch_fde_scan(h, fde_rows, inv_norm, n_pages, q_fde, n_q, scores, ld, static_cast<cudaStream_t>(stream));
 }

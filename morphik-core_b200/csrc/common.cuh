@@ -21,6 +21,15 @@ struct DeviceBuf {  // grow-only device scratch
   size_t cap = 0;
 };
 
+// Which chunk ranges a scoring launch walks.  Full scan: the corpus' own unit plan, scores indexed by page id.
+// Candidate ("slot") mode: unit j = the chunk range of candidate page j, scores indexed by j.
+struct UnitPlan {
+  const int32_t* start = nullptr;
+  const int32_t* end = nullptr;
+  int n_units = 0;
+  int slot_mode = 0;
+};
+
 struct Corpus {
   const void* rows = nullptr;
   int dtype = -1;
@@ -47,6 +56,10 @@ struct b200ms {
   // scratch for pack / search
   bms::DeviceBuf meta_a, meta_b, meta_c;  // small int arrays uploaded per call
   bms::DeviceBuf q_raw, q_packed, scores, mask, out_s, out_i, out_c;
+  bms::DeviceBuf cand_start, cand_end, cand_mask;  // candidate (rerank) mode: per-slot chunk ranges, valid-slot bitmask
+  bms::DeviceBuf fde_simhash, fde_ams_index, fde_ams_sign, fde_tmp;  // FDE configuration (device copies) + scratch
+  int fde_dim = 0, fde_reps = 0, fde_ksim = 0, fde_proj = 0;
+  float fde_scale = 1.f;
   void* pinned = nullptr;  // pinned host staging
   size_t pinned_cap = 0;
   cudaStream_t stream = nullptr;  // internal stream for *_host entry points
@@ -70,10 +83,12 @@ int upload(b200ms_t* h, DeviceBuf& b, const void* src, size_t bytes, cudaStream_
 int make_tmap_rows(b200ms_t* h, CUtensorMap* out, const void* base, int dtype, int64_t n_rows, int box_rows);
 
 // kernel launchers (each returns a b200ms error code and bumps h->launches)
-int launch_score_umma(b200ms_t* h, const void* q_packed, int n_groups_padded, void* group_scores, int64_t ld,
-                      cudaStream_t s);
-int launch_score_b1(b200ms_t* h, const void* q_packed, int n_groups, const int32_t* group_ntok_dev, void* group_scores,
-                    int64_t ld, cudaStream_t s);
+int launch_score_umma(b200ms_t* h, const UnitPlan* plan, const void* q_packed, int n_groups_real, void* group_scores,
+                      int64_t ld, cudaStream_t s);
+int launch_score_b1(b200ms_t* h, const int64_t* cand_ids, int64_t n_cand, const void* q_packed, int n_groups,
+                    const int32_t* group_ntok_dev, void* group_scores, int64_t ld, cudaStream_t s);
+int launch_cand_units(b200ms_t* h, const int64_t* cand_ids, int n_cand, int32_t* unit_start, int32_t* unit_end,
+                      uint32_t* slot_mask, cudaStream_t s);
 int launch_sign_pack(b200ms_t* h, const void* x, int src_dtype, int64_t rows, uint8_t* out, cudaStream_t s);
 int launch_chunk_page(b200ms_t* h, const int64_t* page_start_dev, int64_t n_pages, int32_t* chunk_page, cudaStream_t s);
 int launch_pack_rows(b200ms_t* h, const void* src, int src_dtype, const int64_t* src_start_dev,
@@ -81,7 +96,13 @@ int launch_pack_rows(b200ms_t* h, const void* src, int src_dtype, const int64_t*
                      int dst_dtype, float i8_scale, cudaStream_t s);
 int launch_topk(b200ms_t* h, const void* group_scores, int score_dtype, int64_t n_pages, int64_t ld,
                 const int32_t* group_offsets_dev, int n_q, const uint32_t* allow_mask, int k, float scale,
-                int64_t id_base, float* top_scores, int64_t* top_ids, int32_t* top_counts, cudaStream_t s);
+                int64_t id_base, const int64_t* id_map, float* top_scores, int64_t* top_ids, int32_t* top_counts,
+                cudaStream_t s);
+int launch_fde_encode(b200ms_t* h, const void* rows, int src_dtype, const int64_t* item_start_dev, int n_items,
+                      int is_document, float* out, cudaStream_t s);
+int launch_fde_finalize(b200ms_t* h, const float* fde, int64_t n, void* out_rows, float* inv_norm, cudaStream_t s);
+int launch_fde_scan(b200ms_t* h, const void* F, const float* inv_norm, int64_t n_pages, const float* q_fde, int n_q,
+                    float* scores, int64_t ld, cudaStream_t s);
 int launch_merge_topk(b200ms_t* h, const float* cand_scores, const int64_t* cand_ids, int n_q, int m, int k,
                       float* top_scores, int64_t* top_ids, int32_t* top_counts, cudaStream_t s);
 

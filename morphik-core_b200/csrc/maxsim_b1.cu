@@ -23,6 +23,7 @@ constexpr int kB1Warps = 8;
 template <int G>
 __global__ void __launch_bounds__(kB1Warps * 32)
 maxsim_b1_kernel(const uint4* __restrict__ rows, const int64_t* __restrict__ page_start, int64_t n_pages,
+                 const int64_t* __restrict__ cand_ids /* NULL: every page; else n_pages candidates, output slot = index */,
                  const uint4* __restrict__ q_bits /*[n_groups*32]*/, const int32_t* __restrict__ group_ntok, int g_base,
                  int n_groups, int32_t* __restrict__ group_scores, int64_t ld) {
   __shared__ uint4 slab[kB1Warps][32];
@@ -45,7 +46,8 @@ maxsim_b1_kernel(const uint4* __restrict__ rows, const int64_t* __restrict__ pag
   const int64_t warp_global = int64_t(blockIdx.x) * kB1Warps + warp;
   const int64_t warp_stride = int64_t(gridDim.x) * kB1Warps;
   for (int64_t p = warp_global; p < n_pages; p += warp_stride) {
-    const int64_t r0 = __ldg(page_start + p), r1 = __ldg(page_start + p + 1);
+    const int64_t pg = cand_ids ? __ldg(cand_ids + p) : p;
+    const int64_t r0 = pg >= 0 ? __ldg(page_start + pg) : 0, r1 = pg >= 0 ? __ldg(page_start + pg + 1) : 0;
     int best[G];
 #pragma unroll
     for (int g = 0; g < G; ++g) best[g] = 129;  // min Hamming so far (129 = none)
@@ -78,11 +80,12 @@ maxsim_b1_kernel(const uint4* __restrict__ rows, const int64_t* __restrict__ pag
   }
 }
 
-int launch_score_b1(b200ms_t* h, const void* q_packed, int n_groups, const int32_t* group_ntok_dev, void* group_scores,
-                    int64_t ld, cudaStream_t s) {
+int launch_score_b1(b200ms_t* h, const int64_t* cand_ids, int64_t n_cand, const void* q_packed, int n_groups,
+                    const int32_t* group_ntok_dev, void* group_scores, int64_t ld, cudaStream_t s) {
   const Corpus& c = h->corpus;
-  if (c.n_pages == 0 || n_groups == 0) return B200MS_OK;
-  int64_t want = (c.n_pages + kB1Warps - 1) / kB1Warps;
+  const int64_t n_items = cand_ids ? n_cand : c.n_pages;
+  if (n_items == 0 || n_groups == 0) return B200MS_OK;
+  int64_t want = (n_items + kB1Warps - 1) / kB1Warps;
   const int64_t cap = int64_t(h->num_sms) * 8;
   const int grid = int(want < cap ? want : cap);
   const uint4* rows = static_cast<const uint4*>(c.rows);
@@ -92,16 +95,16 @@ int launch_score_b1(b200ms_t* h, const void* q_packed, int n_groups, const int32
   for (int base = 0; base < n_groups;) {
     const int rem = n_groups - base;
     if (rem >= 8) {
-      maxsim_b1_kernel<8><<<grid, kB1Warps * 32, 0, s>>>(rows, ps, c.n_pages, qb, group_ntok_dev, base, n_groups, out, ld);
+      maxsim_b1_kernel<8><<<grid, kB1Warps * 32, 0, s>>>(rows, ps, n_items, cand_ids, qb, group_ntok_dev, base, n_groups, out, ld);
       base += 8;
     } else if (rem >= 4) {
-      maxsim_b1_kernel<4><<<grid, kB1Warps * 32, 0, s>>>(rows, ps, c.n_pages, qb, group_ntok_dev, base, n_groups, out, ld);
+      maxsim_b1_kernel<4><<<grid, kB1Warps * 32, 0, s>>>(rows, ps, n_items, cand_ids, qb, group_ntok_dev, base, n_groups, out, ld);
       base += 4;
     } else if (rem >= 2) {
-      maxsim_b1_kernel<2><<<grid, kB1Warps * 32, 0, s>>>(rows, ps, c.n_pages, qb, group_ntok_dev, base, n_groups, out, ld);
+      maxsim_b1_kernel<2><<<grid, kB1Warps * 32, 0, s>>>(rows, ps, n_items, cand_ids, qb, group_ntok_dev, base, n_groups, out, ld);
       base += 2;
     } else {
-      maxsim_b1_kernel<1><<<grid, kB1Warps * 32, 0, s>>>(rows, ps, c.n_pages, qb, group_ntok_dev, base, n_groups, out, ld);
+      maxsim_b1_kernel<1><<<grid, kB1Warps * 32, 0, s>>>(rows, ps, n_items, cand_ids, qb, group_ntok_dev, base, n_groups, out, ld);
       base += 1;
     }
     h->launches++;

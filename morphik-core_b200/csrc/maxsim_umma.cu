@@ -73,7 +73,8 @@ template <int KIND, int NM, bool AT>
 __global__ void __launch_bounds__(kThreads, 1)
 maxsim_umma_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constant__ CUtensorMap tmap_q,
                    const void* __restrict__ q_rows, int n_q_rows, const int32_t* __restrict__ chunk_page,
-                   const int32_t* __restrict__ unit_start, int n_units, int m_tile_base, int n_groups_real,
+                   const int32_t* __restrict__ unit_start, const int32_t* __restrict__ unit_end, int slot_mode,
+                   int n_units, int m_tile_base, int n_groups_real,
                    typename Kind<KIND>::Acc* __restrict__ group_scores, int64_t ld, int num_stages) {
   using K = Kind<KIND>;
   using Acc = typename K::Acc;
@@ -137,7 +138,7 @@ maxsim_umma_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_c
       int stage = 0;
       uint32_t phase = 0;
       for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
-        const int c0 = __ldg(unit_start + u), c1 = __ldg(unit_start + u + 1);
+        const int c0 = __ldg(unit_start + u), c1 = __ldg(unit_end + u);
         const int n_tiles = (c1 - c0 + 3) >> 2;
         for (int t = 0; t < n_tiles; ++t) {
           mbar_wait(&empty[stage], phase ^ 1);
@@ -168,7 +169,7 @@ maxsim_umma_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_c
     uint32_t phase = 0;
     uint32_t seq = 0;
     for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
-      const int c0 = __ldg(unit_start + u), c1 = __ldg(unit_start + u + 1);
+      const int c0 = __ldg(unit_start + u), c1 = __ldg(unit_end + u);
       const int n_tiles = (c1 - c0 + 3) >> 2;
       for (int t = 0; t < n_tiles; ++t) {
         mbar_wait(&full[stage], phase);
@@ -255,7 +256,7 @@ maxsim_umma_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_c
       uint32_t tile_seq = 0;
 
       for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
-        const int c0 = __ldg(unit_start + u), c1 = __ldg(unit_start + u + 1);
+        const int c0 = __ldg(unit_start + u), c1 = __ldg(unit_end + u);
         const int n_tiles = (c1 - c0 + 3) >> 2;
 #pragma unroll
         for (int i = 0; i < NMW; ++i) cur_page[i] = -1;
@@ -320,7 +321,7 @@ maxsim_umma_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_c
                 if (pg[j] != cp) {
                   if (cp >= 0) {
                     const Acc s = warp_sum(rm);
-                    if (lane == 0) group_scores[int64_t(group) * ld + cp] = s;
+                    if (lane == 0) group_scores[int64_t(group) * ld + (slot_mode ? u : cp)] = s;
                   }
                   cp = pg[j];
                   rm = cm[j];
@@ -344,7 +345,7 @@ maxsim_umma_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_c
           const int group = (m_tile_base + m) * 4 + quad;
           if (group < n_groups_real && cur_page[i] >= 0) {
             const Acc s = warp_sum(runmax[i]);
-            if (lane == 0) group_scores[int64_t(group) * ld + cur_page[i]] = s;
+            if (lane == 0) group_scores[int64_t(group) * ld + (slot_mode ? u : cur_page[i])] = s;
           }
         }
       }
@@ -361,8 +362,8 @@ maxsim_umma_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_c
 
 // ---------------------------------------------------------------------------------------------- host side
 template <int KIND, int NM, bool AT>
-static int launch_one(b200ms_t* h, const CUtensorMap& tq, const void* q_rows, int n_q_rows, int m_tile_base,
-                      int n_groups_real, void* scores, int64_t ld, cudaStream_t s) {
+static int launch_one(b200ms_t* h, const UnitPlan& up, const CUtensorMap& tq, const void* q_rows, int n_q_rows,
+                      int m_tile_base, int n_groups_real, void* scores, int64_t ld, cudaStream_t s) {
   using K = Kind<KIND>;
   const Corpus& c = h->corpus;
   const uint32_t q_bytes = AT ? 0 : NM * K::kTileBytes;
@@ -376,18 +377,18 @@ static int launch_one(b200ms_t* h, const CUtensorMap& tq, const void* q_rows, in
                          "cudaFuncSetAttribute(maxsim_umma)"))
     return e;
   int grid = h->max_ctas > 0 ? h->max_ctas : h->num_sms;
-  if (grid > c.n_units) grid = c.n_units;
+  if (grid > up.n_units) grid = up.n_units;
   if (grid < 1) return B200MS_OK;
-  kern<<<grid, kThreads, smem, s>>>(c.tmap, tq, q_rows, n_q_rows, static_cast<const int32_t*>(h->chunk_page.p),
-                                   static_cast<const int32_t*>(h->unit_start.p), c.n_units, m_tile_base, n_groups_real,
+  kern<<<grid, kThreads, smem, s>>>(c.tmap, tq, q_rows, n_q_rows, static_cast<const int32_t*>(h->chunk_page.p), up.start,
+                                   up.end, up.slot_mode, up.n_units, m_tile_base, n_groups_real,
                                    static_cast<typename K::Acc*>(scores), ld, stages);
   h->launches++;
   return check_cuda(h, cudaGetLastError(), "launch maxsim_umma");
 }
 
 template <int KIND, bool AT>
-static int launch_kind(b200ms_t* h, const CUtensorMap& tq, const void* q_rows, int n_q_rows, int n_groups_real,
-                       int n_mtiles, void* scores, int64_t ld, cudaStream_t s) {
+static int launch_kind(b200ms_t* h, const UnitPlan& up, const CUtensorMap& tq, const void* q_rows, int n_q_rows,
+                       int n_groups_real, int n_mtiles, void* scores, int64_t ld, cudaStream_t s) {
   // resident query tiles per pass: SS form is bounded by shared memory (bf16 4, s8 8), TS form by the 256 TMEM columns
   // left of the accumulators (bf16 4 x 64 columns, s8 8 x 32 columns)
   constexpr int kMaxNM = KIND == 0 ? 4 : 8;
@@ -398,12 +399,12 @@ static int launch_kind(b200ms_t* h, const CUtensorMap& tq, const void* q_rows, i
     while (nm < rem && nm < kMaxNM) nm <<= 1;  // round up: a phantom (all-zero) tile beats a 2nd pass over the corpus
     int e;
     switch (nm) {
-      case 1: e = launch_one<KIND, 1, AT>(h, tq, q_rows, n_q_rows, base, n_groups_real, scores, ld, s); break;
-      case 2: e = launch_one<KIND, 2, AT>(h, tq, q_rows, n_q_rows, base, n_groups_real, scores, ld, s); break;
-      case 4: e = launch_one<KIND, 4, AT>(h, tq, q_rows, n_q_rows, base, n_groups_real, scores, ld, s); break;
+      case 1: e = launch_one<KIND, 1, AT>(h, up, tq, q_rows, n_q_rows, base, n_groups_real, scores, ld, s); break;
+      case 2: e = launch_one<KIND, 2, AT>(h, up, tq, q_rows, n_q_rows, base, n_groups_real, scores, ld, s); break;
+      case 4: e = launch_one<KIND, 4, AT>(h, up, tq, q_rows, n_q_rows, base, n_groups_real, scores, ld, s); break;
       default:
         if constexpr (KIND == 1) {
-          e = launch_one<KIND, 8, AT>(h, tq, q_rows, n_q_rows, base, n_groups_real, scores, ld, s);
+          e = launch_one<KIND, 8, AT>(h, up, tq, q_rows, n_q_rows, base, n_groups_real, scores, ld, s);
         } else {
           e = set_error(h, B200MS_EINVAL, "maxsim_umma: bad NM");
         }
@@ -414,9 +415,18 @@ static int launch_kind(b200ms_t* h, const CUtensorMap& tq, const void* q_rows, i
   return B200MS_OK;
 }
 
-int launch_score_umma(b200ms_t* h, const void* q_packed, int n_groups_real, void* group_scores, int64_t ld,
-                      cudaStream_t s) {
+int launch_score_umma(b200ms_t* h, const UnitPlan* plan, const void* q_packed, int n_groups_real, void* group_scores,
+                      int64_t ld, cudaStream_t s) {
   const Corpus& c = h->corpus;
+  UnitPlan up;
+  if (plan) {
+    up = *plan;
+  } else {  // full scan: unit u = [unit_start[u], unit_start[u+1])
+    up.start = static_cast<const int32_t*>(h->unit_start.p);
+    up.end = up.start + 1;
+    up.n_units = c.n_units;
+    up.slot_mode = 0;
+  }
   if (!c.has_tmap) return set_error(h, B200MS_ESTATE, "score: corpus has no TMA descriptor");
   const int n_groups_padded = (n_groups_real + 3) & ~3;
   const int n_mtiles = n_groups_padded / 4;
@@ -425,11 +435,11 @@ int launch_score_umma(b200ms_t* h, const void* q_packed, int n_groups_real, void
   if (!ts)
     if (int e = make_tmap_rows(h, &h->tmap_q, q_packed, c.dtype, int64_t(n_q_rows), kTileM)) return e;
   if (c.dtype == B200MS_BF16) {
-    return ts ? launch_kind<0, true>(h, h->tmap_q, q_packed, n_q_rows, n_groups_real, n_mtiles, group_scores, ld, s)
-              : launch_kind<0, false>(h, h->tmap_q, q_packed, n_q_rows, n_groups_real, n_mtiles, group_scores, ld, s);
+    return ts ? launch_kind<0, true>(h, up, h->tmap_q, q_packed, n_q_rows, n_groups_real, n_mtiles, group_scores, ld, s)
+              : launch_kind<0, false>(h, up, h->tmap_q, q_packed, n_q_rows, n_groups_real, n_mtiles, group_scores, ld, s);
   }
-  return ts ? launch_kind<1, true>(h, h->tmap_q, q_packed, n_q_rows, n_groups_real, n_mtiles, group_scores, ld, s)
-            : launch_kind<1, false>(h, h->tmap_q, q_packed, n_q_rows, n_groups_real, n_mtiles, group_scores, ld, s);
+  return ts ? launch_kind<1, true>(h, up, h->tmap_q, q_packed, n_q_rows, n_groups_real, n_mtiles, group_scores, ld, s)
+            : launch_kind<1, false>(h, up, h->tmap_q, q_packed, n_q_rows, n_groups_real, n_mtiles, group_scores, ld, s);
 }
 
 }  // namespace bms

@@ -99,6 +99,32 @@ chunk_page_kernel(const int64_t* __restrict__ page_start, int64_t n_pages, int32
   }
 }
 
+// Candidate (rerank) mode: unit j = chunk range of page cand_ids[j] (empty for id < 0); slot_mask bit j = id valid.
+__global__ void cand_units_kernel(const int64_t* __restrict__ cand_ids, int n_cand, const int64_t* __restrict__ page_start,
+                                  int64_t n_pages, int32_t* __restrict__ unit_start, int32_t* __restrict__ unit_end,
+                                  uint32_t* __restrict__ slot_mask) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t id = j < n_cand ? cand_ids[j] : -1;
+  const bool ok = id >= 0 && id < n_pages;
+  if (j < n_cand && unit_start) {
+    unit_start[j] = ok ? int32_t(page_start[id] / kGroup) : 0;
+    unit_end[j] = ok ? int32_t(page_start[id + 1] / kGroup) : 0;
+  }
+  if (slot_mask) {
+    const uint32_t bal = __ballot_sync(0xffffffffu, ok);
+    if ((threadIdx.x & 31) == 0 && j < n_cand) slot_mask[j >> 5] = bal;
+  }
+}
+
+int launch_cand_units(b200ms_t* h, const int64_t* cand_ids, int n_cand, int32_t* unit_start, int32_t* unit_end,
+                      uint32_t* slot_mask, cudaStream_t s) {
+  if (n_cand <= 0) return B200MS_OK;
+  cand_units_kernel<<<(n_cand + 255) / 256, 256, 0, s>>>(cand_ids, n_cand, static_cast<const int64_t*>(h->page_start.p),
+                                                        h->corpus.n_pages, unit_start, unit_end, slot_mask);
+  h->launches++;
+  return check_cuda(h, cudaGetLastError(), "launch cand_units");
+}
+
 static int grid_for(b200ms_t* h, int64_t warps) {
   int64_t blocks = (warps + 7) / 8;
   const int64_t cap = int64_t(h->num_sms) * 16;

@@ -63,8 +63,8 @@ __device__ void bitonic_desc_u64(uint64_t* a, int n2) {
 template <typename T>
 __global__ void __launch_bounds__(kTopkThreads)
 topk_kernel(const T* __restrict__ gs, int64_t n_pages, int64_t ld, const int32_t* __restrict__ group_offsets,
-            const uint32_t* __restrict__ allow, int k, float scale, int64_t id_base, float* __restrict__ top_scores,
-            int64_t* __restrict__ top_ids, int32_t* __restrict__ top_counts) {
+            const uint32_t* __restrict__ allow, int k, float scale, int64_t id_base, const int64_t* __restrict__ id_map,
+            float* __restrict__ top_scores, int64_t* __restrict__ top_ids, int32_t* __restrict__ top_counts) {
   extern __shared__ uint64_t win[];  // [n2] winners as (key << 32) | (0xffffffff - page)
   __shared__ uint32_t hist[256];
   __shared__ uint32_t s_prefix, s_need, s_total, s_gt, s_eq_base;
@@ -157,7 +157,8 @@ topk_kernel(const T* __restrict__ gs, int64_t n_pages, int64_t ld, const int32_t
     const bool live = uint32_t(i) < kk;
     const uint64_t w = live ? win[i] : 0;
     top_scores[int64_t(q) * k + i] = live ? score_of_key(uint32_t(w >> 32), T(0)) * scale : -CUDART_INF_F;
-    top_ids[int64_t(q) * k + i] = live ? int64_t(0xffffffffu - uint32_t(w)) + id_base : int64_t(-1);
+    const int64_t slot = int64_t(0xffffffffu - uint32_t(w));
+    top_ids[int64_t(q) * k + i] = live ? (id_map ? __ldg(id_map + slot) : slot + id_base) : int64_t(-1);
   }
   if (tid == 0) top_counts[q] = int32_t(kk);
 }
@@ -222,19 +223,20 @@ merge_topk_kernel(const float* __restrict__ cand_scores, const int64_t* __restri
 
 int launch_topk(b200ms_t* h, const void* group_scores, int score_dtype, int64_t n_pages, int64_t ld,
                 const int32_t* group_offsets_dev, int n_q, const uint32_t* allow_mask, int k, float scale,
-                int64_t id_base, float* top_scores, int64_t* top_ids, int32_t* top_counts, cudaStream_t s) {
+                int64_t id_base, const int64_t* id_map, float* top_scores, int64_t* top_ids, int32_t* top_counts,
+                cudaStream_t s) {
   if (n_q <= 0) return B200MS_OK;
   int n2 = 1;
   while (n2 < k) n2 <<= 1;
   const size_t smem = size_t(n2) * sizeof(uint64_t);
   if (score_dtype == B200MS_F32) {
     topk_kernel<float><<<n_q, kTopkThreads, smem, s>>>(static_cast<const float*>(group_scores), n_pages, ld,
-                                                      group_offsets_dev, allow_mask, k, scale, id_base, top_scores,
-                                                      top_ids, top_counts);
+                                                      group_offsets_dev, allow_mask, k, scale, id_base, id_map,
+                                                      top_scores, top_ids, top_counts);
   } else {
     topk_kernel<int><<<n_q, kTopkThreads, smem, s>>>(static_cast<const int*>(group_scores), n_pages, ld,
-                                                    group_offsets_dev, allow_mask, k, scale, id_base, top_scores,
-                                                    top_ids, top_counts);
+                                                    group_offsets_dev, allow_mask, k, scale, id_base, id_map,
+                                                    top_scores, top_ids, top_counts);
   }
   h->launches++;
   return check_cuda(h, cudaGetLastError(), "launch topk");

@@ -1,0 +1,249 @@
+"""Fixed-dimensional encodings (MUVERA FDE) + two-stage search: FDE candidate scan -> exact MaxSim rerank.
+
+API mirror of the reference's ``fixed_dimensional_encoding`` extension module as Morphik uses it
+(core/vector_store/fast_multivector_store.py:325-331, 447-449, 521):
+
+    cfg = FixedDimensionalEncodingConfig(dimension=128, num_repetitions=20, num_simhash_projections=5,
+                                         projection_dimension=16, projection_type="AMS_SKETCH")
+    q_fde = generate_query_encoding(q, cfg)        # np.ndarray [n,128] -> np.float32 [10240]
+    d_fde = generate_document_encoding(p, cfg)
+
+and ``TwoStageIndex``, which replaces stages 1-4 of FastMultiVectorStore.query_similar (:521-557): the query FDE, the
+Turbopuffer ANN over document FDEs (cosine distance, ``top_k = min(10*k, 75)`` there; any candidate count here), the
+gather of candidate multivectors and the MaxSim rerank -- all on the GPU, with the multivectors already resident.
+
+PARITY NOTE: the extension's C++ sources are not in the reference snapshot, so the exact random streams of
+the upstream implementation (std::mt19937 based) cannot be reproduced or checked here.  The construction (SimHash
+partitions with Gray-code index, AMS sketch, SUM for queries / AVERAGE for documents, empty partitions zero) follows the
+published algorithm; the matrices come from ``numpy.random.default_rng(seed + repetition)``.  FDEs produced here are
+therefore self-consistent (query and document sides share the matrices) but NOT interchangeable with vectors already
+stored in a Turbopuffer namespace by the reference.
+"""
+from __future__ import annotations
+
+import ctypes
+import threading
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _native as nat
+from .index import MaxSimIndex, _vp
+
+
+@dataclass(frozen=True)
+class FixedDimensionalEncodingConfig:
+    dimension: int = 128
+    num_repetitions: int = 20
+    num_simhash_projections: int = 5
+    projection_dimension: int = 16
+    projection_type: str = "AMS_SKETCH"
+    seed: int = 1
+    fill_empty_partitions: bool = False
+
+    @property
+    def num_partitions(self) -> int:
+        return 1 << self.num_simhash_projections
+
+    @property
+    def fde_dimension(self) -> int:
+        return self.num_repetitions * self.num_partitions * self.projection_dimension
+
+    @property
+    def scale(self) -> float:
+        return 1.0 / float(np.sqrt(self.projection_dimension))
+
+    def validate(self) -> None:
+        if self.dimension != nat.DIM:
+            raise ValueError(f"dimension must be {nat.DIM}")
+        if self.projection_type != "AMS_SKETCH":
+            raise ValueError("only projection_type='AMS_SKETCH' (the reference's setting) is implemented")
+        if self.fill_empty_partitions:
+            raise ValueError("fill_empty_partitions=True is not implemented (the reference leaves it at the default False)")
+
+
+def fde_matrices(cfg: FixedDimensionalEncodingConfig) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """(simhash [R,128,K] float32 Gaussian, ams_index [R,128] int32 in [0,proj), ams_sign [R,128] float32 +-1)."""
+    cfg.validate()
+    R, K, P = cfg.num_repetitions, cfg.num_simhash_projections, cfg.projection_dimension
+    simhash = np.empty((R, cfg.dimension, K), dtype=np.float32)
+    ams_index = np.empty((R, cfg.dimension), dtype=np.int32)
+    ams_sign = np.empty((R, cfg.dimension), dtype=np.float32)
+    for r in range(R):
+        rng = np.random.default_rng(cfg.seed + r)
+        simhash[r] = rng.standard_normal((cfg.dimension, K)).astype(np.float32)
+        ams_index[r] = rng.integers(0, P, size=cfg.dimension).astype(np.int32)
+        ams_sign[r] = np.where(rng.integers(0, 2, size=cfg.dimension) == 1, 1.0, -1.0).astype(np.float32)
+    return simhash, ams_index, ams_sign
+
+
+def configure_handle(index: MaxSimIndex, cfg: FixedDimensionalEncodingConfig) -> None:
+    simhash, ams_index, ams_sign = fde_matrices(cfg)
+    index.h.check(
+        nat.lib.b200ms_fde_configure(index.h.ptr, cfg.num_repetitions, cfg.num_simhash_projections, cfg.projection_dimension,
+                                     ctypes.c_float(cfg.scale), simhash.ctypes.data_as(ctypes.c_void_p),
+                                     ams_index.ctypes.data_as(ctypes.c_void_p), ams_sign.ctypes.data_as(ctypes.c_void_p)),
+        "b200ms_fde_configure")
+
+
+def encode_items(index: MaxSimIndex, items: Sequence, is_document: bool, fde_dim: int) -> torch.Tensor:
+    """FDEs of ragged [n_i,128] items -> float32 device tensor [len(items), fde_dim] (one kernel launch per 65535 items)."""
+    out = torch.empty((len(items), fde_dim), dtype=torch.float32, device=index.device)
+    step = 65535
+    for i0 in range(0, len(items), step):
+        part = items[i0:i0 + step]
+        lens = [int(x.shape[0]) for x in part]
+        src, src_dtype = index._stage_rows(part)
+        with torch.cuda.device(index.device):
+            index.h.check(
+                nat.lib.b200ms_fde_encode(index.h.ptr, _vp(src), src_dtype, nat.i32_array(lens), len(lens), int(is_document),
+                                          _vp(out[i0:i0 + len(part)]), index._stream()),
+                "b200ms_fde_encode")
+    return out
+
+
+# ------------------------------------------------------------------ module-level API (drop-in for the extension module)
+_default_lock = threading.Lock()
+_default_encoders: Dict[Tuple[int, FixedDimensionalEncodingConfig], MaxSimIndex] = {}
+
+
+def _encoder(cfg: FixedDimensionalEncodingConfig, device: int = 0) -> MaxSimIndex:
+    with _default_lock:
+        key = (device, cfg)
+        if key not in _default_encoders:
+            idx = MaxSimIndex(device=device, dtype="bf16")  # only its handle/stream are used
+            configure_handle(idx, cfg)
+            _default_encoders[key] = idx
+        return _default_encoders[key]
+
+
+def generate_query_encoding(point_cloud, config: FixedDimensionalEncodingConfig, device: int = 0) -> np.ndarray:
+    """fde.generate_query_encoding(np.ndarray [n,128], cfg) -> np.float32 [fde_dimension] (fast_multivector_store.py:521)."""
+    x = np.ascontiguousarray(np.asarray(point_cloud, dtype=np.float32).reshape(-1, nat.DIM))
+    idx = _encoder(config, device)
+    return encode_items(idx, [x], False, config.fde_dimension)[0].cpu().numpy()
+
+
+def generate_document_encoding(point_cloud, config: FixedDimensionalEncodingConfig, device: int = 0) -> np.ndarray:
+    """fde.generate_document_encoding(np.ndarray [n,128], cfg) (fast_multivector_store.py:447-449)."""
+    x = np.ascontiguousarray(np.asarray(point_cloud, dtype=np.float32).reshape(-1, nat.DIM))
+    idx = _encoder(config, device)
+    return encode_items(idx, [x], True, config.fde_dimension)[0].cpu().numpy()
+
+
+# ------------------------------------------------------------------ two-stage index
+class TwoStageIndex:
+    """MaxSimIndex + a dense FDE matrix [N, fde_dim] bf16 with per-row inverse norms.
+
+    search(): query FDE (device) -> exhaustive cosine scan of the FDE matrix (HBM-bound, 2*fde_dim bytes per page) -> top
+    ``n_candidates`` per query -> exact MaxSim over those pages only (b200ms_rerank_device) -> top-k.
+    """
+
+    def __init__(self, device: int = 0, dtype: str = "bf16", config: Optional[FixedDimensionalEncodingConfig] = None):
+        self.cfg = config or FixedDimensionalEncodingConfig()
+        self.index = MaxSimIndex(device=device, dtype=dtype)
+        configure_handle(self.index, self.cfg)
+        self.device = self.index.device
+        self.fde_dim = self.cfg.fde_dimension
+        self._F: Optional[torch.Tensor] = None  # bf16 [cap, fde_dim]
+        self._inv: Optional[torch.Tensor] = None  # float32 [cap]
+        self._n = 0
+        self.last_timing_ms: Dict[str, float] = {}
+
+    @property
+    def n_pages(self) -> int:
+        return self._n
+
+    def _grow(self, need: int) -> None:
+        cap = 0 if self._F is None else self._F.shape[0]
+        if need <= cap:
+            return
+        new_cap = max(need, int(cap * 1.5), 256)
+        F = torch.empty((new_cap, self.fde_dim), dtype=torch.bfloat16, device=self.device)
+        inv = torch.empty((new_cap,), dtype=torch.float32, device=self.device)
+        if self._n:
+            F[: self._n].copy_(self._F[: self._n])
+            inv[: self._n].copy_(self._inv[: self._n])
+        self._F, self._inv = F, inv
+
+    def add_pages(self, pages: Sequence) -> Tuple[int, int]:
+        first, n = self.index.add_pages(pages)
+        if n == 0:
+            return first, 0
+        fde = encode_items(self.index, list(pages), True, self.fde_dim)
+        self._grow(self._n + n)
+        with torch.cuda.device(self.device):
+            self.index.h.check(
+                nat.lib.b200ms_fde_finalize(self.index.h.ptr, _vp(fde), n, _vp(self._F[self._n:]), _vp(self._inv[self._n:]),
+                                            self.index._stream()),
+                "b200ms_fde_finalize")
+        self._n += n
+        return first, n
+
+    def fde_scores(self, q_fde: torch.Tensor) -> torch.Tensor:
+        """[n_q, fde_dim] float32 device -> cosine-ranking scores [n_q, ld] (ld >= n_pages)."""
+        n_q = q_fde.shape[0]
+        ld = max((self._n + 31) // 32 * 32, 32)
+        scores = torch.empty((n_q, ld), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            self.index.h.check(
+                nat.lib.b200ms_fde_scan(self.index.h.ptr, _vp(self._F), _vp(self._inv), self._n, _vp(q_fde.contiguous()), n_q,
+                                        _vp(scores), ld, self.index._stream()),
+                "b200ms_fde_scan")
+        return scores
+
+    def candidates(self, queries: Sequence, n_candidates: int):
+        """First stage only: (candidate page ids int64 [n_q, n_candidates] (-1 padded), FDE scores, counts) on the device."""
+        n_q = len(queries)
+        q_fde = encode_items(self.index, list(queries), False, self.fde_dim)
+        scores = self.fde_scores(q_fde)
+        kk = int(min(n_candidates, nat.MAX_K))
+        ts = torch.empty((n_q, kk), dtype=torch.float32, device=self.device)
+        ti = torch.empty((n_q, kk), dtype=torch.int64, device=self.device)
+        tc = torch.empty((n_q,), dtype=torch.int32, device=self.device)
+        goff = nat.i32_array(list(range(n_q + 1)))
+        with torch.cuda.device(self.device):
+            self.index.h.check(
+                nat.lib.b200ms_topk(self.index.h.ptr, _vp(scores), nat.F32, self._n, scores.shape[1], goff, n_q, None, kk,
+                                    ctypes.c_float(1.0), 0, _vp(ts), _vp(ti), _vp(tc), self.index._stream()),
+                "b200ms_topk(fde)")
+        return ti, ts, tc
+
+    def rerank(self, query, cand_ids: torch.Tensor, k: int):
+        """Exact MaxSim of ONE query over the candidate pages (device int64 [n_cand], -1 = unused) -> top-k."""
+        self.index._attach()
+        src, src_dtype = self.index._stage_rows([query])
+        n_cand = int(cand_ids.numel())
+        kk = int(min(k, n_cand))
+        ts = torch.empty((1, kk), dtype=torch.float32, device=self.device)
+        ti = torch.empty((1, kk), dtype=torch.int64, device=self.device)
+        tc = torch.empty((1,), dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            self.index.h.check(
+                nat.lib.b200ms_rerank_device(self.index.h.ptr, _vp(src), src_dtype, nat.i32_array([int(query.shape[0])]), 1,
+                                             _vp(cand_ids.contiguous()), n_cand, kk, ctypes.c_float(self.index.i8_scale),
+                                             ctypes.c_float(self.index.score_scale), _vp(ts), _vp(ti), _vp(tc),
+                                             self.index._stream()),
+                "b200ms_rerank_device")
+        return ts, ti, tc
+
+    def search(self, queries: Sequence, k: int, n_candidates: int = 1000):
+        """Two-stage search; returns host arrays (scores [n_q,k], page ids [n_q,k], counts [n_q]) and fills last_timing_ms."""
+        n_q = len(queries)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        ev[0].record()
+        cand, _, _ = self.candidates(queries, n_candidates)
+        ev[1].record()
+        out_s = np.full((n_q, k), -np.inf, dtype=np.float32)
+        out_i = np.full((n_q, k), -1, dtype=np.int64)
+        out_c = np.zeros((n_q,), dtype=np.int32)
+        results = [self.rerank(q, cand[qi], k) for qi, q in enumerate(queries)]
+        ev[2].record()
+        torch.cuda.synchronize(self.device)
+        for qi, (ts, ti, tc) in enumerate(results):
+            n = ts.shape[1]
+            out_s[qi, :n], out_i[qi, :n], out_c[qi] = ts[0].cpu().numpy(), ti[0].cpu().numpy(), int(tc[0])
+        self.last_timing_ms = {"fde_candidates_ms": ev[0].elapsed_time(ev[1]), "maxsim_rerank_ms": ev[1].elapsed_time(ev[2])}
+        return out_s, out_i, out_c

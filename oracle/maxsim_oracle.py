@@ -34,8 +34,8 @@ _lib = None
 
 def build_c_oracle(force: bool = False) -> str:
     """Compile maxsim_oracle.c (gcc) into oracle/_build/liboracle.so; returns the path."""
-    src = os.path.join(_HERE, "maxsim_oracle.c")
-    stale = (not os.path.exists(_LIB_PATH)) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src)
+    srcs = [os.path.join(_HERE, f) for f in ("maxsim_oracle.c", "fde_oracle.c", "Makefile")]
+    stale = (not os.path.exists(_LIB_PATH)) or any(os.path.getmtime(_LIB_PATH) < os.path.getmtime(f) for f in srcs)
     if force or stale:
         subprocess.run(["make", "-C", _HERE, "-s"] + (["-B"] if force else []), check=True)
     return _LIB_PATH
@@ -56,6 +56,7 @@ def c_oracle() -> ctypes.CDLL:
         lib.oracle_int8_maxsim.argtypes = [vp, i32, vp, vp, i64, i32, vp]
         lib.oracle_topk.argtypes = [vp, i64, vp, i64, vp, vp]
         lib.oracle_topk.restype = i64
+        lib.oracle_fde_encode.argtypes = [vp, i64, i32, i32, i32, i32, ctypes.c_float, vp, vp, vp, i32, vp]
         _lib = lib
     return _lib
 
@@ -261,3 +262,48 @@ def score_multi_vector_port_dense(q: "np.ndarray", p: "np.ndarray", batch_size: 
             row.append(torch.einsum("bnd,csd->bcns", tq[i:i + batch_size], tp[j:j + batch_size]).max(dim=3)[0].sum(dim=2))
         out.append(torch.cat(row, dim=1))
     return torch.cat(out, dim=0)
+
+
+# ------------------------------------------------------------------------------------------------
+# FDE (MUVERA) -- parity unpinned (sources absent from the reference); see oracle/fde_oracle.c
+# ------------------------------------------------------------------------------------------------
+def fde_encode_c(x: np.ndarray, simhash: np.ndarray, ams_index: np.ndarray, ams_sign: np.ndarray, scale: float,
+                 is_document: bool) -> np.ndarray:
+    """x [n,128] float32 -> FDE float32 [reps * 2^ksim * proj] with the loop order the device kernel uses."""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    simhash = np.ascontiguousarray(simhash, dtype=np.float32)
+    ams_index = np.ascontiguousarray(ams_index, dtype=np.int32)
+    ams_sign = np.ascontiguousarray(ams_sign, dtype=np.float32)
+    reps, dim, ksim = simhash.shape
+    proj = int(ams_index.max()) + 1 if ams_index.size else 1
+    return fde_encode_c_proj(x, simhash, ams_index, ams_sign, scale, is_document, proj)
+
+
+def fde_encode_c_proj(x, simhash, ams_index, ams_sign, scale, is_document, proj) -> np.ndarray:
+    reps, dim, ksim = simhash.shape
+    out = np.zeros(reps * (1 << ksim) * proj, dtype=np.float32)
+    c_oracle().oracle_fde_encode(_ptr(x), x.shape[0], dim, reps, ksim, proj, ctypes.c_float(scale), _ptr(simhash),
+                                 _ptr(ams_index), _ptr(ams_sign), int(is_document), _ptr(out))
+    return out
+
+
+def fde_encode_np(x: np.ndarray, simhash: np.ndarray, ams_index: np.ndarray, ams_sign: np.ndarray, scale: float,
+                  is_document: bool, proj: int) -> np.ndarray:
+    """Independent numpy restatement (float64 arithmetic) used to cross-check the C loops within rounding."""
+    x = np.asarray(x, dtype=np.float64)
+    reps, dim, ksim = simhash.shape
+    n_part = 1 << ksim
+    out = np.zeros((reps, n_part, proj))
+    for r in range(reps):
+        bits = (np.asarray(x, dtype=np.float32) @ simhash[r].astype(np.float32)) > 0  # [n, ksim]
+        code = np.zeros(x.shape[0], dtype=np.int64)
+        for k in range(ksim):
+            code = (code << 1) + (bits[:, k].astype(np.int64) ^ (code & 1))
+        A = np.zeros((dim, proj))
+        A[np.arange(dim), ams_index[r]] = ams_sign[r]
+        y = x @ A
+        for p in range(n_part):
+            sel = code == p
+            if sel.any():
+                out[r, p] = y[sel].sum(axis=0) * scale / (sel.sum() if is_document else 1.0)
+    return out.reshape(-1).astype(np.float32)
