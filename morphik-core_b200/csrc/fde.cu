@@ -149,19 +149,33 @@ fde_scan_kernel(const uint4* __restrict__ F, const float* __restrict__ inv_norm,
 #pragma unroll
     for (int q = 0; q < kFdeQ; ++q) acc[q] = 0.f;
     const uint4* row = F + p * vec_per_row;
-    for (int v = lane; v < vec_per_row; v += 32) {
-      const uint4 w = __ldg(row + v);
-      float f[8];
-      f[0] = __uint_as_float(w.x << 16); f[1] = __uint_as_float(w.x & 0xffff0000u);
-      f[2] = __uint_as_float(w.y << 16); f[3] = __uint_as_float(w.y & 0xffff0000u);
-      f[4] = __uint_as_float(w.z << 16); f[5] = __uint_as_float(w.z & 0xffff0000u);
-      f[6] = __uint_as_float(w.w << 16); f[7] = __uint_as_float(w.w & 0xffff0000u);
+    // 4 independent 16-byte loads in flight per lane (the scan is latency-bound otherwise: one warp per 20 KB row)
+    for (int v0 = lane; v0 < vec_per_row; v0 += 128) {
+      uint4 w[4];
 #pragma unroll
-      for (int q = 0; q < kFdeQ; ++q) {
-        if (q < nq_here) {
-          const float* qq = s_q + q * fde_dim + v * 8;
+      for (int u = 0; u < 4; ++u) {
+        const int v = v0 + 32 * u;
+        w[u] = v < vec_per_row ? __ldg(row + v) : make_uint4(0, 0, 0, 0);
+      }
 #pragma unroll
-          for (int e = 0; e < 8; ++e) acc[q] = fmaf(f[e], qq[e], acc[q]);
+      for (int u = 0; u < 4; ++u) {
+        const int v = v0 + 32 * u;
+        if (v >= vec_per_row) break;
+        float f[8];
+        f[0] = __uint_as_float(w[u].x << 16); f[1] = __uint_as_float(w[u].x & 0xffff0000u);
+        f[2] = __uint_as_float(w[u].y << 16); f[3] = __uint_as_float(w[u].y & 0xffff0000u);
+        f[4] = __uint_as_float(w[u].z << 16); f[5] = __uint_as_float(w[u].z & 0xffff0000u);
+        f[6] = __uint_as_float(w[u].w << 16); f[7] = __uint_as_float(w[u].w & 0xffff0000u);
+#pragma unroll
+        for (int q = 0; q < kFdeQ; ++q) {
+          if (q < nq_here) {
+            const float4* qq = reinterpret_cast<const float4*>(s_q + q * fde_dim + v * 8);
+            const float4 q0 = qq[0], q1 = qq[1];
+            acc[q] = fmaf(f[0], q0.x, acc[q]); acc[q] = fmaf(f[1], q0.y, acc[q]);
+            acc[q] = fmaf(f[2], q0.z, acc[q]); acc[q] = fmaf(f[3], q0.w, acc[q]);
+            acc[q] = fmaf(f[4], q1.x, acc[q]); acc[q] = fmaf(f[5], q1.y, acc[q]);
+            acc[q] = fmaf(f[6], q1.z, acc[q]); acc[q] = fmaf(f[7], q1.w, acc[q]);
+          }
         }
       }
     }
@@ -200,12 +214,16 @@ int launch_fde_finalize(b200ms_t* h, const float* fde, int64_t n, void* out_rows
 int launch_fde_scan(b200ms_t* h, const void* F, const float* inv_norm, int64_t n_pages, const float* q_fde, int n_q,
                     float* scores, int64_t ld, cudaStream_t s) {
   if (n_pages <= 0 || n_q <= 0) return B200MS_OK;
-  const size_t smem = size_t(kFdeQ) * h->fde_dim * sizeof(float);
+  const int nq_res = n_q < kFdeQ ? n_q : kFdeQ;  // queries resident per launch
+  const size_t smem = size_t(nq_res) * h->fde_dim * sizeof(float);
   if (int e = check_cuda(h, cudaFuncSetAttribute(fde_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)),
                          "cudaFuncSetAttribute(fde_scan)"))
     return e;
+  int per_sm = int((220 * 1024) / (smem + 1024));  // CTAs per SM by shared memory (40 KB per resident query)
+  if (per_sm < 1) per_sm = 1;
+  if (per_sm > 8) per_sm = 8;
   int64_t blocks = (n_pages + 7) / 8;
-  if (blocks > int64_t(h->num_sms)) blocks = h->num_sms;  // one 256-thread CTA per SM (160 KB of query data in smem)
+  if (blocks > int64_t(h->num_sms) * per_sm) blocks = int64_t(h->num_sms) * per_sm;
   for (int qb = 0; qb < n_q; qb += kFdeQ) {
     fde_scan_kernel<<<int(blocks), 256, smem, s>>>(static_cast<const uint4*>(F), inv_norm, n_pages, h->fde_dim, q_fde, n_q, qb,
                                                    scores, ld);

@@ -182,6 +182,31 @@ class TwoStageIndex:
         self._n += n
         return first, n
 
+    def adopt_packed(self, rows: torch.Tensor, page_lens: Sequence[int], batch_pages: int = 16384) -> None:
+        """Adopt an already packed bf16 device corpus (see MaxSimIndex.adopt_packed) and build its FDE matrix from the packed
+        rows directly.  Requires every page length to be a multiple of 32 (no padding rows inside the packed buffer)."""
+        lens = [int(x) for x in page_lens]
+        if self.index.dtype != nat.BF16 or any(n % 32 for n in lens):
+            raise ValueError("adopt_packed needs a bf16 corpus whose page lengths are multiples of 32")
+        self.index.adopt_packed(rows, lens)
+        n = len(lens)
+        self._grow(n)
+        flat = rows.view(torch.uint8).reshape(-1)
+        tmp = torch.empty((min(batch_pages, max(n, 1)), self.fde_dim), dtype=torch.float32, device=self.device)
+        row0 = 0
+        with torch.cuda.device(self.device):
+            for i0 in range(0, n, batch_pages):
+                part = lens[i0:i0 + batch_pages]
+                src = flat[row0 * 256:]
+                self.index.h.check(
+                    nat.lib.b200ms_fde_encode(self.index.h.ptr, _vp(src), nat.BF16, nat.i32_array(part), len(part), 1, _vp(tmp),
+                                              self.index._stream()), "b200ms_fde_encode")
+                self.index.h.check(
+                    nat.lib.b200ms_fde_finalize(self.index.h.ptr, _vp(tmp), len(part), _vp(self._F[i0:]), _vp(self._inv[i0:]),
+                                                self.index._stream()), "b200ms_fde_finalize")
+                row0 += sum(part)
+        self._n = n
+
     def fde_scores(self, q_fde: torch.Tensor) -> torch.Tensor:
         """[n_q, fde_dim] float32 device -> cosine-ranking scores [n_q, ld] (ld >= n_pages)."""
         n_q = q_fde.shape[0]
@@ -194,8 +219,19 @@ class TwoStageIndex:
                 "b200ms_fde_scan")
         return scores
 
-    def candidates(self, queries: Sequence, n_candidates: int):
-        """First stage only: (candidate page ids int64 [n_q, n_candidates] (-1 padded), FDE scores, counts) on the device."""
+    def compact(self, keep: Sequence[int]) -> None:
+        """Keep only pages `keep` (ascending old ids) in both the patch corpus and the FDE matrix."""
+        keep_t = torch.as_tensor([int(p) for p in keep], dtype=torch.int64, device=self.device)
+        self.index.compact(keep)
+        if self._F is not None and len(keep):
+            self._F = self._F[: self._n].index_select(0, keep_t).contiguous()
+            self._inv = self._inv[: self._n].index_select(0, keep_t).contiguous()
+        self._n = len(keep)
+
+    def candidates(self, queries: Sequence, n_candidates: int, allow_mask_dev: Optional[torch.Tensor] = None):
+        """First stage only: (candidate page ids int64 [n_q, n_candidates] (-1 padded), FDE scores, counts) on the device.
+        allow_mask_dev: optional uint32 page bitmask (the doc_ids filter, applied BEFORE candidate selection like the
+        reference's Turbopuffer filter, fast_multivector_store.py:527)."""
         n_q = len(queries)
         q_fde = encode_items(self.index, list(queries), False, self.fde_dim)
         scores = self.fde_scores(q_fde)
@@ -206,7 +242,8 @@ class TwoStageIndex:
         goff = nat.i32_array(list(range(n_q + 1)))
         with torch.cuda.device(self.device):
             self.index.h.check(
-                nat.lib.b200ms_topk(self.index.h.ptr, _vp(scores), nat.F32, self._n, scores.shape[1], goff, n_q, None, kk,
+                nat.lib.b200ms_topk(self.index.h.ptr, _vp(scores), nat.F32, self._n, scores.shape[1], goff, n_q,
+                                    _vp(allow_mask_dev), kk,
                                     ctypes.c_float(1.0), 0, _vp(ts), _vp(ti), _vp(tc), self.index._stream()),
                 "b200ms_topk(fde)")
         return ti, ts, tc
@@ -229,12 +266,14 @@ class TwoStageIndex:
                 "b200ms_rerank_device")
         return ts, ti, tc
 
-    def search(self, queries: Sequence, k: int, n_candidates: int = 1000):
-        """Two-stage search; returns host arrays (scores [n_q,k], page ids [n_q,k], counts [n_q]) and fills last_timing_ms."""
+    def search(self, queries: Sequence, k: int, n_candidates: int = 1000, allow_mask: Optional[np.ndarray] = None):
+        """Two-stage search; returns host arrays (scores [n_q,k], page ids [n_q,k], counts [n_q]) and fills last_timing_ms.
+        allow_mask: optional uint32 words (page bitmask) restricting BOTH stages."""
         n_q = len(queries)
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
         ev[0].record()
-        cand, _, _ = self.candidates(queries, n_candidates)
+        mask_dev = None if allow_mask is None else torch.from_numpy(np.ascontiguousarray(allow_mask, dtype=np.uint32).view(np.int32)).to(self.device)
+        cand, _, _ = self.candidates(queries, n_candidates, mask_dev)
         ev[1].record()
         out_s = np.full((n_q, k), -np.inf, dtype=np.float32)
         out_i = np.full((n_q, k), -1, dtype=np.int64)

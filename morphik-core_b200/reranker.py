@@ -1,0 +1,49 @@
+"""MaxSim reranker adapter.
+
+The reference's ``core/reranker`` is a TEXT cross-encoder (``BaseReranker.rerank(query: str, chunks)`` /
+``compute_score(query: str, text)``, core/reranker/base_reranker.py:7-26) and is bypassed when ColPali retrieval is on
+(core/services/document_service.py:381-383).  A late-interaction reranker needs embeddings, not strings, so
+this adapter keeps the method names and result conventions (chunks come back sorted by descending ``score``) but takes the
+query's multivector: "retrieve with any store, rerank with ColPali MaxSim on the GPU".
+"""
+from __future__ import annotations
+
+from typing import List, Sequence, Union
+
+import numpy as np
+
+from .index import MaxSimIndex
+from .models import DocumentChunk
+from .store import as_query_matrix
+
+
+class B200MaxSimReranker:
+    def __init__(self, device: int = 0, mode: str = "bf16"):
+        self.device, self.mode = int(device), mode
+
+    def _scores(self, query_embedding, page_embeddings: Sequence) -> np.ndarray:
+        idx = MaxSimIndex(device=self.device, dtype=self.mode)
+        try:
+            idx.add_pages([np.asarray(e, dtype=np.float32).reshape(-1, 128) for e in page_embeddings])
+            return idx.score_matrix([as_query_matrix(query_embedding)])[0]
+        finally:
+            idx.close()
+
+    async def rerank(self, query_embedding, chunks: List[DocumentChunk]) -> List[DocumentChunk]:
+        """Chunks must carry their multivector in ``embedding``; returns them sorted by MaxSim score (descending, stable)."""
+        if not chunks:
+            return []
+        scores = self._scores(query_embedding, [c.embedding for c in chunks])
+        order = sorted(range(len(chunks)), key=lambda i: (-scores[i], i))
+        out = []
+        for i in order:
+            c = chunks[i].model_copy() if hasattr(chunks[i], "model_copy") else chunks[i]
+            c.score = float(scores[i])
+            out.append(c)
+        return out
+
+    async def compute_score(self, query_embedding, page_embedding: Union[np.ndarray, Sequence]) -> Union[float, List[float]]:
+        """One page ([P,128]) -> float; a list of pages -> list of floats (mirrors BaseReranker.compute_score's two forms)."""
+        if isinstance(page_embedding, (list, tuple)) and len(page_embedding) and np.ndim(page_embedding[0]) == 2:
+            return [float(s) for s in self._scores(query_embedding, page_embedding)]
+        return float(self._scores(query_embedding, [page_embedding])[0])

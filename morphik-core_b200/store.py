@@ -84,7 +84,8 @@ class B200MultiVectorStore(BaseVectorStore):
     """Exhaustive ColPali MaxSim store on one B200 (see module docstring)."""
 
     def __init__(self, uri: str = "b200://0", device: int = 0, mode: str = "bf16", storage: Any = None,
-                 auto_initialize: bool = True, compact_dead_fraction: float = 0.3, index: Any = None):
+                 auto_initialize: bool = True, compact_dead_fraction: float = 0.3, index: Any = None,
+                 fde_candidates: Optional[int] = None):
         self.uri = uri
         self.device = int(device)
         self.mode = mode
@@ -92,6 +93,10 @@ class B200MultiVectorStore(BaseVectorStore):
         self.compact_dead_fraction = float(compact_dead_fraction)
         self.catalog = PageCatalog()
         self._index = index  # injectable for host-logic tests; the product builds a MaxSimIndex in initialize()
+        # None: exhaustive MaxSim over every authorised page (Postgres-provider behaviour).  An int: two-stage search like
+        # the "morphik" provider -- FDE candidates (the reference asks Turbopuffer for min(10*k, 75)) then MaxSim rerank.
+        self.fde_candidates = fde_candidates
+        self._two_stage = None
         self._lock = threading.Lock()
         self._last_store_metrics: Dict[str, Any] = {}
         self.last_query_timing: Dict[str, float] = {}
@@ -103,7 +108,13 @@ class B200MultiVectorStore(BaseVectorStore):
         if self._index is None:
             from .index import MaxSimIndex  # raises when libb200ms.so or the GPU is missing: no silent fallback
 
-            self._index = MaxSimIndex(device=self.device, dtype=self.mode)
+            if self.fde_candidates:
+                from .fde import TwoStageIndex
+
+                self._two_stage = TwoStageIndex(device=self.device, dtype=self.mode)
+                self._index = self._two_stage.index
+            else:
+                self._index = MaxSimIndex(device=self.device, dtype=self.mode)
         return True
 
     def close(self) -> None:
@@ -142,7 +153,7 @@ class B200MultiVectorStore(BaseVectorStore):
 
     def _add_pages_locked(self, valid, app_id):
         with self._lock:
-            first, n = self._index.add_pages([e for _, e in valid])
+            first, n = (self._two_stage or self._index).add_pages([e for _, e in valid])
             for i, (c, e) in enumerate(valid):
                 pid = self.catalog.add(PageRecord(c.document_id, int(c.chunk_number), c.content, dict(c.metadata or {}),
                                                   app_id, int(e.shape[0])))
@@ -186,6 +197,8 @@ class B200MultiVectorStore(BaseVectorStore):
 
     def _search_locked(self, queries, k, words):
         with self._lock:
+            if self._two_stage is not None:
+                return self._two_stage.search(queries, k, n_candidates=max(int(self.fde_candidates), k), allow_mask=words)
             return self._index.search_host(queries, k, allow_mask=words)
 
     async def get_chunks_by_id(self, chunk_identifiers: List[Tuple[str, int]], app_id: Optional[str] = None,
@@ -218,6 +231,40 @@ class B200MultiVectorStore(BaseVectorStore):
     def _compact_locked(self):
         """Drop tombstoned pages: rebuild the device corpus from the surviving packed rows (device-to-device)."""
         keep, _ = self.catalog.compaction_plan()
-        if hasattr(self._index, "compact"):
-            self._index.compact(keep)
+        target = self._two_stage or self._index
+        if hasattr(target, "compact"):
+            target.compact(keep)
         self.catalog.apply_compaction(keep)
+
+    # ------------------------------------------------------------------ persistence (SURVEY 8f-2)
+    def save(self, directory: str) -> None:
+        """Packed shard file + catalogue (JSON lines).  Tombstoned pages are compacted away first."""
+        import os
+
+        from . import shardfile
+
+        os.makedirs(directory, exist_ok=True)
+        with self._lock:
+            if self.catalog.dead_fraction > 0:
+                self._compact_locked()
+            shardfile.save_index(self._index, os.path.join(directory, "corpus.b2ms"))
+            with open(os.path.join(directory, "catalog.jsonl"), "w") as f:
+                for r in self.catalog.records:
+                    f.write(json.dumps({"document_id": r.document_id, "chunk_number": r.chunk_number, "content": r.content,
+                                        "metadata": r.metadata, "app_id": r.app_id, "n_rows": r.n_rows}) + "\n")
+
+    @classmethod
+    def load(cls, directory: str, device: int = 0, **kw) -> "B200MultiVectorStore":
+        import os
+
+        from . import shardfile
+
+        index = shardfile.load_index(os.path.join(directory, "corpus.b2ms"), device=device)
+        store = cls(device=device, mode=index.dtype_name, auto_initialize=False, index=index, **kw)
+        with open(os.path.join(directory, "catalog.jsonl")) as f:
+            for line in f:
+                d = json.loads(line)
+                store.catalog.add(PageRecord(d["document_id"], d["chunk_number"], d["content"], d["metadata"], d["app_id"], d["n_rows"]))
+        if len(store.catalog) != index.n_pages:
+            raise ValueError("catalogue and shard file disagree on the page count")
+        return store

@@ -115,3 +115,41 @@ def test_binary_scores_equal_sql_max_sim_oracle():
     assert [(r.document_id, r.chunk_number) for r in res] == [(f"doc{i // 4}", i % 4) for i in wi]
     assert [r.score for r in res] == ws.tolist()
     store.close()
+
+
+def test_save_load_round_trip(tmp_path):
+    store = B200MultiVectorStore(mode="bf16")
+    rng = np.random.default_rng(8)
+    chunks = [DocumentChunk(document_id=f"d{i // 3}", content=f"content {i}", chunk_number=i % 3, metadata={"i": i},
+                            embedding=rng.standard_normal((int(rng.integers(1, 80)), 128)).astype(np.float32)) for i in range(30)]
+    run(store.store_embeddings(chunks, app_id="app"))
+    run(store.delete_chunks_by_document_id("d4"))  # leaves tombstones (10 % dead: no automatic compaction)
+    q = rng.standard_normal((32, 128)).astype(np.float32)
+    before = run(store.query_similar(q, k=27))
+    store.save(str(tmp_path))
+    loaded = B200MultiVectorStore.load(str(tmp_path))
+    after = run(loaded.query_similar(q, k=27))
+    assert [(r.document_id, r.chunk_number, r.content, r.metadata, r.score) for r in after] == \
+           [(r.document_id, r.chunk_number, r.content, r.metadata, r.score) for r in before]
+    assert len(loaded.catalog) == 27 and run(loaded.get_chunks_by_id([("d4", 0)])) == []
+    store.close(); loaded.close()
+
+
+def test_two_stage_store_matches_exhaustive_when_candidates_cover_corpus():
+    rng = np.random.default_rng(12)
+    chunks = [DocumentChunk(document_id=f"d{i % 7}", content=str(i), chunk_number=i, metadata={},
+                            embedding=rng.standard_normal((int(rng.integers(5, 60)), 128)).astype(np.float32)) for i in range(60)]
+    ex = B200MultiVectorStore(mode="bf16")
+    two = B200MultiVectorStore(mode="bf16", fde_candidates=64)  # >= corpus size: the rerank sees every page
+    run(ex.store_embeddings(chunks)); run(two.store_embeddings(chunks))
+    q = rng.standard_normal((20, 128)).astype(np.float32)
+    for doc_ids in (None, ["d1", "d3"]):
+        a = run(ex.query_similar(q, k=8, doc_ids=doc_ids))
+        b = run(two.query_similar(q, k=8, doc_ids=doc_ids))
+        assert [(r.document_id, r.chunk_number) for r in a] == [(r.document_id, r.chunk_number) for r in b]
+        np.testing.assert_allclose([r.score for r in a], [r.score for r in b], rtol=1e-6)
+    run(two.delete_chunks_by_document_id("d1")); run(two.delete_chunks_by_document_id("d2")); run(two.delete_chunks_by_document_id("d3"))
+    run(ex.delete_chunks_by_document_id("d1")); run(ex.delete_chunks_by_document_id("d2")); run(ex.delete_chunks_by_document_id("d3"))
+    a, b = run(ex.query_similar(q, k=8)), run(two.query_similar(q, k=8))
+    assert [(r.document_id, r.chunk_number) for r in a] == [(r.document_id, r.chunk_number) for r in b]
+    ex.close(); two.close()
