@@ -84,6 +84,10 @@ int64_t b200ms_query_groups(const int32_t* q_lens, int n_q);
 /* x: device [rows,128] F32|BF16 -> out: device [rows,16] sign bits, bit = (float32(x) > 0), MSB first. */
 int b200ms_sign_pack(b200ms_t* h, const void* x, int src_dtype, int64_t rows, uint8_t* out, void* stream);
 
+/* out[i] = popcount(q_bits XOR cand_bits[i]) for one packed 16-byte query row against n packed candidate rows (device,
+ * 16-byte aligned): fast_ops.hamming_distance_batch (core/utils/fast_ops.py:242-248, binary_ops.rs:266-292). */
+int b200ms_hamming_batch(b200ms_t* h, const uint8_t* q_bits, const uint8_t* cand_bits, int64_t n, uint32_t* out, void* stream);
+
 /* Convert n_pages pages stored back to back at src (device, [sum len,128] F32|BF16) into the padded
  * corpus layout at dst (device): page i occupies padded_len(len_i) rows, the padding rows repeat the
  * page's last true row (max-/min-invariant, so scores are unchanged).  dst_dtype BF16: round-to-nearest-even;

@@ -44,6 +44,7 @@ def _load() -> ctypes.CDLL:
         "b200ms_row_bytes": (c_int64, [c_int]),
         "b200ms_query_groups": (c_int64, [i32p, c_int]),
         "b200ms_sign_pack": (c_int, [vp, vp, c_int, c_int64, vp, vp]),
+        "b200ms_hamming_batch": (c_int, [vp, vp, vp, c_int64, vp, vp]),
         "b200ms_pack_pages": (c_int, [vp, vp, c_int, i32p, c_int64, vp, c_int, c_float, vp]),
         "b200ms_set_corpus": (c_int, [vp, vp, c_int, i32p, c_int64]),
         "b200ms_corpus_pages": (c_int64, [vp]),
@@ -82,7 +83,7 @@ EXPORTED = [
     "b200ms_score", "b200ms_topk", "b200ms_merge_topk", "b200ms_search_host", "b200ms_search_device",
     "b200ms_launch_count", "b200ms_last_score_ms", "b200ms_set_tuning", "b200ms_score_call_count",
     "b200ms_score_times_ms", "b200ms_set_option", "b200ms_rerank_device", "b200ms_fde_configure", "b200ms_fde_dim",
-    "b200ms_fde_encode", "b200ms_fde_finalize", "b200ms_fde_scan",
+    "b200ms_fde_encode", "b200ms_fde_finalize", "b200ms_fde_scan", "b200ms_hamming_batch",
 ]
 
 

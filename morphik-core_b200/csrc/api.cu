@@ -266,6 +266,16 @@ B200MS_API int b200ms_sign_pack(b200ms_t* h, const void* x, int src_dtype, int64
   return launch_pack_rows(h, x, src_dtype, d, d, 1, rows, 0, out, B200MS_B1, 1.f, s);
 }
 
+B200MS_API int b200ms_hamming_batch(b200ms_t* h, const uint8_t* q_bits, const uint8_t* cand_bits, int64_t n, uint32_t* out,
+                                    void* stream) {
+  if (!h) return B200MS_EINVAL;
+  if (n < 0 || (n > 0 && (!q_bits || !cand_bits || !out)) || (reinterpret_cast<uintptr_t>(q_bits) & 15) ||
+      (reinterpret_cast<uintptr_t>(cand_bits) & 15))
+    return set_error(h, B200MS_EINVAL, "hamming_batch: bad arguments (16-byte aligned packed rows)");
+  DeviceGuard g(h->device);
+  return launch_hamming_batch(h, q_bits, cand_bits, n, out, static_cast<cudaStream_t>(stream));
+}
+
 B200MS_API int b200ms_pack_pages(b200ms_t* h, const void* src, int src_dtype, const int32_t* page_lens, int64_t n_pages,
                                  void* dst, int dst_dtype, float i8_scale, void* stream) {
   if (!h) return B200MS_EINVAL;

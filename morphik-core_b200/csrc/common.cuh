@@ -89,6 +89,7 @@ int launch_score_b1(b200ms_t* h, const int64_t* cand_ids, int64_t n_cand, const 
                     const int32_t* group_ntok_dev, void* group_scores, int64_t ld, cudaStream_t s);
 int launch_cand_units(b200ms_t* h, const int64_t* cand_ids, int n_cand, int32_t* unit_start, int32_t* unit_end,
                       uint32_t* slot_mask, cudaStream_t s);
+int launch_hamming_batch(b200ms_t* h, const void* q, const void* cand, int64_t n, uint32_t* out, cudaStream_t s);
 int launch_sign_pack(b200ms_t* h, const void* x, int src_dtype, int64_t rows, uint8_t* out, cudaStream_t s);
 int launch_chunk_page(b200ms_t* h, const int64_t* page_start_dev, int64_t n_pages, int32_t* chunk_page, cudaStream_t s);
 int launch_pack_rows(b200ms_t* h, const void* src, int src_dtype, const int64_t* src_start_dev,

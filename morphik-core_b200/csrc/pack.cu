@@ -125,6 +125,26 @@ int launch_cand_units(b200ms_t* h, const int64_t* cand_ids, int n_cand, int32_t*
   return check_cuda(h, cudaGetLastError(), "launch cand_units");
 }
 
+// hamming_distance_batch (core/utils/fast_ops.py:242-248, morphik_rust/src/binary_ops.rs:266-292): popcount(q XOR c_i)
+// of one packed 16-byte query against n packed candidates -- one thread per candidate, 128-bit loads.
+__global__ void __launch_bounds__(256)
+hamming_batch_kernel(const uint4* __restrict__ q, const uint4* __restrict__ cand, int64_t n, uint32_t* __restrict__ out) {
+  const uint4 qq = __ldg(q);
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
+    const uint4 c = __ldg(cand + i);
+    out[i] = __popc(c.x ^ qq.x) + __popc(c.y ^ qq.y) + __popc(c.z ^ qq.z) + __popc(c.w ^ qq.w);
+  }
+}
+
+int launch_hamming_batch(b200ms_t* h, const void* q, const void* cand, int64_t n, uint32_t* out, cudaStream_t s) {
+  if (n <= 0) return B200MS_OK;
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > int64_t(h->num_sms) * 8) blocks = int64_t(h->num_sms) * 8;
+  hamming_batch_kernel<<<int(blocks), 256, 0, s>>>(static_cast<const uint4*>(q), static_cast<const uint4*>(cand), n, out);
+  h->launches++;
+  return check_cuda(h, cudaGetLastError(), "launch hamming_batch");
+}
+
 static int grid_for(b200ms_t* h, int64_t warps) {
   int64_t blocks = (warps + 7) / 8;
   const int64_t cap = int64_t(h->num_sms) * 16;

@@ -358,6 +358,30 @@ class MaxSimIndex:
                          "b200ms_sign_pack")
         return out[:n]
 
+    def hamming_distance_batch(self, query_bits, candidate_bits) -> torch.Tensor:
+        """fast_ops.hamming_distance_batch on the device: packed 16-byte query (bytes / uint8[16]) vs packed candidates
+        (list of bytes / uint8 [n,16]) -> int32 tensor [n] of Hamming distances."""
+        q = np.frombuffer(bytes(query_bits), dtype=np.uint8) if isinstance(query_bits, (bytes, bytearray)) else np.asarray(query_bits, np.uint8)
+        if isinstance(candidate_bits, (list, tuple)):
+            lens = {len(c) for c in candidate_bits}
+            if lens - {16}:
+                raise ValueError(f"Vector length mismatch: candidates must be 16 bytes like the query, got {sorted(lens)}")
+            c = np.frombuffer(b"".join(bytes(x) for x in candidate_bits), dtype=np.uint8).reshape(-1, 16)
+        else:
+            c = candidate_bits
+        if q.size != 16:
+            raise ValueError(f"Vector length mismatch: {q.size} vs 16")  # ValueError like the Rust implementation
+        qd = torch.from_numpy(q.reshape(16).copy()).to(self.device)
+        cd = c if isinstance(c, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(c, dtype=np.uint8)).to(self.device)
+        cd = cd.contiguous().view(-1, 16)
+        qa = _aligned_bytes(16, self.device, 16); qa.copy_(qd)
+        ca = _aligned_bytes(max(cd.numel(), 16), self.device, 16); ca[: cd.numel()].copy_(cd.reshape(-1))
+        out = torch.empty((cd.shape[0],), dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            self.h.check(nat.lib.b200ms_hamming_batch(self.h.ptr, _vp(qa), _vp(ca), cd.shape[0], _vp(out), self._stream()),
+                         "b200ms_hamming_batch")
+        return out
+
     def merge_topk(self, cand_scores: torch.Tensor, cand_ids: torch.Tensor, k: int):
         """Merge candidate lists [n_q, m] (ids < 0 ignored) -> top-k by (score desc, id asc), on the device."""
         n_q, m = cand_scores.shape

@@ -57,6 +57,20 @@ def test_sign_pack_matches_reference_golden(golden_dir):
     assert np.array_equal(idx.sign_pack(big).cpu().numpy(), orc.sign_pack_c(big))
 
 
+def test_hamming_distance_batch_matches_reference_golden(golden_dir):
+    sp = np.load(os.path.join(golden_dir, "sign_pack.npz"))  # ham_batch was produced by the reference's fast_ops.py
+    idx = MaxSimIndex(dtype="binary")
+    got = idx.hamming_distance_batch(bytes(sp["ham_a"][0]), [bytes(r) for r in sp["ham_b"]]).cpu().numpy()
+    assert np.array_equal(got, sp["ham_batch"])
+    a = np.array([0b11110000, 0b10101010] + [0] * 14, dtype=np.uint8)  # binary_ops.rs:322-333 -> 8
+    b = np.array([[0b11110000, 0b01010101] + [0] * 14], dtype=np.uint8)
+    assert idx.hamming_distance_batch(a, b).cpu().tolist() == [8]
+    big = np.random.default_rng(0).integers(0, 256, size=(100003, 16), dtype=np.uint8)
+    assert np.array_equal(idx.hamming_distance_batch(big[7], big).cpu().numpy(), orc.hamming_np(big[7][None, :], big))
+    with pytest.raises(ValueError, match="length mismatch"):
+        idx.hamming_distance_batch(b"\x00" * 16, [b"\x00" * 15])
+
+
 # ------------------------------------------------------------------------------------------------ float MaxSim (a-7)
 def test_bf16_config0_shape_single_query():
     # BASELINE config 0: 100 pages x 1024 patches x 128-d, one 32-token query
