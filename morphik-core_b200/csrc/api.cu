@@ -148,6 +148,7 @@ B200MS_API int b200ms_create(int device, b200ms_t** out) {
   h->device = device;
   h->num_sms = prop.multiProcessorCount;
   if (const char* e = getenv("B200MS_A_IN_TMEM")) h->a_in_tmem = atoi(e) != 0;
+  if (const char* e = getenv("B200MS_B1_TENSOR")) h->b1_tensor = atoi(e);
   if (int e = check_cuda(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking), "cudaStreamCreate")) {
     delete h;
     return e;
@@ -166,7 +167,7 @@ B200MS_API int b200ms_destroy(b200ms_t* h) {
   cudaDeviceSynchronize();
   DeviceBuf* bufs[] = {&h->chunk_page, &h->unit_start, &h->page_start, &h->meta_a, &h->meta_b, &h->meta_c, &h->q_raw,
                        &h->q_packed, &h->scores, &h->mask, &h->out_s, &h->out_i, &h->out_c, &h->cand_start, &h->cand_end,
-                       &h->cand_mask, &h->fde_simhash, &h->fde_ams_index, &h->fde_ams_sign, &h->fde_tmp};
+                       &h->cand_mask, &h->b1_q_i8, &h->b1_tok_const, &h->fde_simhash, &h->fde_ams_index, &h->fde_ams_sign, &h->fde_tmp};
   for (DeviceBuf* b : bufs)
     if (b->p) cudaFree(b->p);
   if (h->pinned) cudaFreeHost(h->pinned);
@@ -217,6 +218,8 @@ B200MS_API int b200ms_set_option(b200ms_t* h, const char* name, int64_t value) {
   const std::string n(name);
   if (n == "a_in_tmem") {
     h->a_in_tmem = value != 0;
+  } else if (n == "b1_tensor" && value >= 0 && value <= 2) {
+    h->b1_tensor = int(value);
   } else if (n == "unit_rows" && value > 0) {
     h->unit_rows = value;
   } else if (n == "max_ctas" && value >= 0) {
@@ -385,10 +388,20 @@ static int score_impl(b200ms_t* h, const void* q_packed, int n_groups, const int
       }
     }
     if (int e = upload(h, h->meta_c, ntok.data(), ntok.size() * 4, s)) return e;
+    // b1_tensor: 0 = POPC kernel, 1 = tcgen05 kernel, 2 (default) = measured crossover: one 32-token group is faster on the
+    // POPC pipe (1.59 vs 2.49 ms / 65536 pages), two or more groups on the tensor cores (a 128-token tile costs the same
+    // as one token there).  Rerank of a candidate list stays on the POPC kernel.
+    const bool tensor_path = !cand_ids && (h->b1_tensor == 1 || (h->b1_tensor == 2 && n_groups >= 2));
+    if (tensor_path && c.has_empty)
+      if (int e = check_cuda(h, cudaMemsetAsync(group_scores, 0, size_t(n_groups_padded) * size_t(ld) * 4, s), "score: memset")) return e;
     cudaEventRecord(h->ev0[slot], s);
-    if (int e = launch_score_b1(h, cand_ids, n_cand, q_packed, n_groups, static_cast<const int32_t*>(h->meta_c.p),
-                                group_scores, ld, s))
-      return e;
+    if (tensor_path) {
+      if (int e = launch_score_b1_umma(h, q_packed, static_cast<const int32_t*>(h->meta_c.p), n_groups, group_scores, ld, s)) return e;
+    } else {
+      if (int e = launch_score_b1(h, cand_ids, n_cand, q_packed, n_groups, static_cast<const int32_t*>(h->meta_c.p),
+                                  group_scores, ld, s))
+        return e;
+    }
     cudaEventRecord(h->ev1[slot], s);
     h->ev_count++;
     // ntok is pageable host memory: the async upload staged it before returning, nothing else to wait for

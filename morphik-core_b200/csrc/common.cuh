@@ -56,6 +56,7 @@ struct b200ms {
   // scratch for pack / search
   bms::DeviceBuf meta_a, meta_b, meta_c;  // small int arrays uploaded per call
   bms::DeviceBuf q_raw, q_packed, scores, mask, out_s, out_i, out_c;
+  bms::DeviceBuf b1_q_i8, b1_tok_const;  // tensor-core 1-bit scorer: +-1 int8 query tiles and per-token constants
   bms::DeviceBuf cand_start, cand_end, cand_mask;  // candidate (rerank) mode: per-slot chunk ranges, valid-slot bitmask
   bms::DeviceBuf fde_simhash, fde_ams_index, fde_ams_sign, fde_tmp;  // FDE configuration (device copies) + scratch
   int fde_dim = 0, fde_reps = 0, fde_ksim = 0, fde_proj = 0;
@@ -70,6 +71,7 @@ struct b200ms {
   int64_t launches = 0;
   int64_t unit_rows = 4096;
   int max_ctas = 0;
+  int b1_tensor = 2;  // 1-bit corpora: 0 = POPC kernel, 1 = tcgen05 kernel (bits expanded to {0,1} int8 in smem), 2 = auto
   int a_in_tmem = 0;  // 1: feed the query operand of tcgen05.mma from TMEM (TS form), 0: from shared memory (SS form)
   CUtensorMap tmap_q;  // rebuilt per score call
 };
@@ -87,6 +89,8 @@ int launch_score_umma(b200ms_t* h, const UnitPlan* plan, const void* q_packed, i
                       int64_t ld, cudaStream_t s);
 int launch_score_b1(b200ms_t* h, const int64_t* cand_ids, int64_t n_cand, const void* q_packed, int n_groups,
                     const int32_t* group_ntok_dev, void* group_scores, int64_t ld, cudaStream_t s);
+int launch_score_b1_umma(b200ms_t* h, const void* q_bits, const int32_t* group_ntok_dev, int n_groups_real,
+                         void* group_scores, int64_t ld, cudaStream_t s);
 int launch_cand_units(b200ms_t* h, const int64_t* cand_ids, int n_cand, int32_t* unit_start, int32_t* unit_end,
                       uint32_t* slot_mask, cudaStream_t s);
 int launch_hamming_batch(b200ms_t* h, const void* q, const void* cand, int64_t n, uint32_t* out, cudaStream_t s);

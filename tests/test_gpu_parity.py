@@ -188,13 +188,15 @@ def test_binary_known_answers_from_reference_tests(golden_dir):
         assert ti[0][0] == j and ts[0][0] == 3.0 and np.all(np.diff(ts[0]) <= 0)
 
 
+@pytest.mark.parametrize("path", [0, 1, 2])  # 0 = POPC kernel, 1 = tcgen05 kernel (incl. the replicated-query form), 2 = auto
 @pytest.mark.parametrize("n_q", [1, 3, 8, 13])
-def test_binary_bit_exact(n_q):
+def test_binary_bit_exact(n_q, path):
     rng = np.random.default_rng(50 + n_q)
     lens = [1, 31, 32, 33, 0, 64, 1024, 5, 700] + list(rng.integers(1, 200, size=50))
     pages = make_pages(rng, lens)
     queries = [unit_rows(rng, t) for t in ([32, 7, 45, 1, 20, 64, 33, 32, 2, 9, 100, 31, 32][:n_q])]
     idx = MaxSimIndex(dtype="binary")
+    idx.set_option("b1_tensor", path)
     idx.add_pages(pages)
     got = idx.score_matrix(queries)
     d_bits = orc.sign_pack_c(np.concatenate(pages))
