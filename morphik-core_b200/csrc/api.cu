@@ -149,6 +149,7 @@ B200MS_API int b200ms_create(int device, b200ms_t** out) {
   h->num_sms = prop.multiProcessorCount;
   if (const char* e = getenv("B200MS_A_IN_TMEM")) h->a_in_tmem = atoi(e) != 0;
   if (const char* e = getenv("B200MS_B1_TENSOR")) h->b1_tensor = atoi(e);
+  if (const char* e = getenv("B200MS_SPLIT4")) h->split4 = atoi(e);
   if (int e = check_cuda(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking), "cudaStreamCreate")) {
     delete h;
     return e;
@@ -218,6 +219,8 @@ B200MS_API int b200ms_set_option(b200ms_t* h, const char* name, int64_t value) {
   const std::string n(name);
   if (n == "a_in_tmem") {
     h->a_in_tmem = value != 0;
+  } else if (n == "split4" && value >= 0 && value <= 2) {
+    h->split4 = int(value);
   } else if (n == "b1_tensor" && value >= 0 && value <= 2) {
     h->b1_tensor = int(value);
   } else if (n == "unit_rows" && value > 0) {

@@ -33,7 +33,7 @@ constexpr int kThreads = 384;
 constexpr int kNumAccum = 4;                     // TMEM accumulators, kTileN fp32 columns each (4*128 = 512)
 constexpr uint32_t kSubtileBytes = 128 * 128;    // 128 rows x 128 B (one swizzle-128B panel)
 constexpr uint32_t kSmemLimit = 232448;          // 227 KB opt-in maximum per CTA
-constexpr uint32_t kBarrierBytes = 1024;
+constexpr uint32_t kBarrierBytes = 2048;         // mbarriers + TMEM slot + the S4 exchange slab
 
 template <int KIND>
 struct Kind {
@@ -69,7 +69,11 @@ __device__ __forceinline__ Acc chunk_max(const uint32_t (&v)[32]) {
 // AT = true : A (queries) staged ONCE into TMEM columns [0, 64*NM) by tcgen05.st and fed from there ("TS" form), 4
 //             accumulators of 64 columns at [256, 512): the tensor core then reads only B from shared memory
 //             (64 B/clk instead of 128 B/clk at the nominal MMA rate) and the query tiles free 32 KB * NM of smem.
-template <int KIND, int NM, bool AT>
+// S4 (NM == 1, SS form, ONE 32-token group -- the single-query case): the 32 query rows are TMA-loaded into all four
+//             32-row quarters of the tile, so every lane quadrant of the accumulator holds the same tokens and each of the
+//             four epilogue warps reduces one 32-column chunk in parallel (instead of warp 0 walking all four); the chunk
+//             maxima meet in a shared-memory slab once per tile and warp 0 applies the page logic.
+template <int KIND, int NM, bool AT, bool S4>
 __global__ void __launch_bounds__(kThreads, 1)
 maxsim_umma_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constant__ CUtensorMap tmap_q,
                    const void* __restrict__ q_rows, int n_q_rows, const int32_t* __restrict__ chunk_page,
@@ -97,6 +101,7 @@ maxsim_umma_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_c
   uint64_t* tempty = bars + 40;              // [kNumAccum]  epilogue -> MMA
   uint64_t* qfull = bars + 48;               // query tiles landed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 56);
+  uint32_t* slab = reinterpret_cast<uint32_t*>(bars + 64);  // S4: [2][4][32] chunk maxima (raw bits)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -128,12 +133,20 @@ maxsim_umma_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_c
       if constexpr (!AT) {
         const uint64_t pol_q = policy_evict_last();
         mbar_expect_tx(qfull, NM * K::kTileBytes);
-#pragma unroll
-        for (int m = 0; m < NM; ++m)
+        if constexpr (S4) {  // tmap_q has 32-row boxes: the group's 32 token rows land in all four row quarters
 #pragma unroll
           for (int p = 0; p < K::kPanels; ++p)
-            tma_load_2d(&tmap_q, qfull, smem_q + m * K::kTileBytes + p * kSubtileBytes, p * K::kPanelElems,
-                        (m_tile_base + m) * kTileM, pol_q);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              tma_load_2d(&tmap_q, qfull, smem_q + p * kSubtileBytes + j * 4096, p * K::kPanelElems, m_tile_base * kTileM, pol_q);
+        } else {
+#pragma unroll
+          for (int m = 0; m < NM; ++m)
+#pragma unroll
+            for (int p = 0; p < K::kPanels; ++p)
+              tma_load_2d(&tmap_q, qfull, smem_q + m * K::kTileBytes + p * kSubtileBytes, p * K::kPanelElems,
+                          (m_tile_base + m) * kTileM, pol_q);
+        }
       }
       int stage = 0;
       uint32_t phase = 0;
@@ -250,7 +263,57 @@ maxsim_umma_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_c
       }
     }
 
-    if (wg < NWG) {
+    if constexpr (S4) {
+      if (wg == 0) {
+        const int group = m_tile_base * 4;
+        Acc rm = Acc(0);
+        int cp = -1;
+        uint32_t seq = 0;
+        for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+          const int c0 = __ldg(unit_start + u), c1 = __ldg(unit_end + u);
+          const int n_tiles = (c1 - c0 + 3) >> 2;
+          for (int t = 0; t < n_tiles; ++t, ++seq) {
+            const uint32_t buf = seq & (kNumAccum - 1);
+            mbar_wait(&tfull[buf], (seq >> 2) & 1);
+            tc_fence_after();
+            uint32_t va[32];
+            tmem_ld_32x32(lane_base + kAccCol0 + buf * kAccN + quad * 32, va);  // chunk `quad` of this quadrant's copy
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[buf]);
+            uint32_t* sl = slab + (seq & 1) * 128;
+            const Acc mine = chunk_max<Acc>(va);
+            sl[quad * 32 + lane] = *reinterpret_cast<const uint32_t*>(&mine);
+            asm volatile("bar.sync 1, 128;" ::: "memory");  // the four warps of epilogue warpgroup 0
+            if (quad == 0) {
+              const int cb = c0 + 4 * t;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                if (cb + j >= c1) break;
+                const int pgj = __ldg(chunk_page + cb + j);
+                const Acc v = acc_from_bits(sl[j * 32 + lane], Acc{});
+                if (pgj != cp) {
+                  if (cp >= 0) {
+                    const Acc s2 = warp_sum(rm);
+                    if (lane == 0) group_scores[int64_t(group) * ld + (slot_mode ? u : cp)] = s2;
+                  }
+                  cp = pgj;
+                  rm = v;
+                } else {
+                  rm = acc_max(rm, v);
+                }
+              }
+            }
+          }
+          if (quad == 0 && cp >= 0) {  // unit ends on a page boundary
+            const Acc s2 = warp_sum(rm);
+            if (lane == 0) group_scores[int64_t(group) * ld + (slot_mode ? u : cp)] = s2;
+          }
+          cp = -1;
+        }
+      }
+    } else if (wg < NWG) {
       Acc runmax[NMW];
       int cur_page[NMW];
       uint32_t tile_seq = 0;
@@ -361,7 +424,7 @@ maxsim_umma_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_c
 }
 
 // ---------------------------------------------------------------------------------------------- host side
-template <int KIND, int NM, bool AT>
+template <int KIND, int NM, bool AT, bool S4 = false>
 static int launch_one(b200ms_t* h, const UnitPlan& up, const CUtensorMap& tq, const void* q_rows, int n_q_rows,
                       int m_tile_base, int n_groups_real, void* scores, int64_t ld, cudaStream_t s) {
   using K = Kind<KIND>;
@@ -372,7 +435,7 @@ static int launch_one(b200ms_t* h, const UnitPlan& up, const CUtensorMap& tq, co
   if (stages > 8) stages = 8;
   if (stages < 2) return set_error(h, B200MS_EINVAL, "maxsim_umma: not enough shared memory for 2 stages");
   const uint32_t smem = 1024 + q_bytes + uint32_t(stages) * K::kTileBytes + kBarrierBytes;
-  auto kern = maxsim_umma_kernel<KIND, NM, AT>;
+  auto kern = maxsim_umma_kernel<KIND, NM, AT, S4>;
   if (int e = check_cuda(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)),
                          "cudaFuncSetAttribute(maxsim_umma)"))
     return e;
@@ -432,6 +495,14 @@ int launch_score_umma(b200ms_t* h, const UnitPlan* plan, const void* q_packed, i
   const int n_mtiles = n_groups_padded / 4;
   const int n_q_rows = n_groups_padded * kGroup;
   const bool ts = h->a_in_tmem != 0;
+  // Single 32-token group: replicated-query form (32-row TMA boxes).  Measured at 65536 pages: bf16 2.40 vs 2.51-2.59 ms
+  // (7.2 TB/s), but int8 1.65 vs 1.42 ms -- so split4 = 1 (default) enables it for bf16 only, 2 forces it for both.
+  if (!ts && n_groups_real == 1 && (h->split4 == 2 || (h->split4 == 1 && c.dtype == B200MS_BF16))) {
+    if (int e = make_tmap_rows(h, &h->tmap_q, q_packed, c.dtype, int64_t(n_q_rows), 32)) return e;
+    return c.dtype == B200MS_BF16
+               ? launch_one<0, 1, false, true>(h, up, h->tmap_q, q_packed, n_q_rows, 0, n_groups_real, group_scores, ld, s)
+               : launch_one<1, 1, false, true>(h, up, h->tmap_q, q_packed, n_q_rows, 0, n_groups_real, group_scores, ld, s);
+  }
   if (!ts)
     if (int e = make_tmap_rows(h, &h->tmap_q, q_packed, c.dtype, int64_t(n_q_rows), kTileM)) return e;
   if (c.dtype == B200MS_BF16) {

@@ -72,6 +72,20 @@ def test_hamming_distance_batch_matches_reference_golden(golden_dir):
 
 
 # ------------------------------------------------------------------------------------------------ float MaxSim (a-7)
+@pytest.mark.parametrize("dtype,split4", [("bf16", 0), ("bf16", 2), ("int8", 0), ("int8", 2)])
+def test_single_group_forms_agree(dtype, split4):
+    """The replicated-query (split4) and the plain epilogue of maxsim_umma give bit-identical single-query scores."""
+    rng = np.random.default_rng(77)
+    lens = [1, 31, 32, 33, 0, 64, 127, 128, 129, 700, 1030, 2] + list(rng.integers(1, 400, size=40))
+    pages = make_pages(rng, lens)
+    for t in (32, 5):
+        q = [unit_rows(rng, t)]
+        ref = MaxSimIndex(dtype=dtype); ref.set_option("split4", 1 if dtype == "int8" else 0); ref.set_option("unit_rows", 300)
+        alt = MaxSimIndex(dtype=dtype); alt.set_option("split4", split4); alt.set_option("unit_rows", 300)
+        ref.add_pages(pages); alt.add_pages(pages)
+        assert np.array_equal(ref.score_matrix(q), alt.score_matrix(q))
+
+
 def test_bf16_config0_shape_single_query():
     # BASELINE config 0: 100 pages x 1024 patches x 128-d, one 32-token query
     rng = np.random.default_rng(1234)
