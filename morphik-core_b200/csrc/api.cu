@@ -168,7 +168,7 @@ B200MS_API int b200ms_destroy(b200ms_t* h) {
   cudaDeviceSynchronize();
   DeviceBuf* bufs[] = {&h->chunk_page, &h->unit_start, &h->page_start, &h->meta_a, &h->meta_b, &h->meta_c, &h->q_raw,
                        &h->q_packed, &h->scores, &h->mask, &h->out_s, &h->out_i, &h->out_c, &h->cand_start, &h->cand_end,
-                       &h->cand_mask, &h->b1_q_i8, &h->b1_tok_const, &h->fde_simhash, &h->fde_ams_index, &h->fde_ams_sign, &h->fde_tmp};
+                       &h->cand_mask, &h->topk_keys, &h->topk_ids, &h->b1_q_i8, &h->b1_tok_const, &h->fde_simhash, &h->fde_ams_index, &h->fde_ams_sign, &h->fde_tmp};
   for (DeviceBuf* b : bufs)
     if (b->p) cudaFree(b->p);
   if (h->pinned) cudaFreeHost(h->pinned);

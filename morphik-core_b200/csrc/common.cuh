@@ -56,6 +56,7 @@ struct b200ms {
   // scratch for pack / search
   bms::DeviceBuf meta_a, meta_b, meta_c;  // small int arrays uploaded per call
   bms::DeviceBuf q_raw, q_packed, scores, mask, out_s, out_i, out_c;
+  bms::DeviceBuf topk_keys, topk_ids;  // first-level (per-slice) top-k candidates
   bms::DeviceBuf b1_q_i8, b1_tok_const;  // tensor-core 1-bit scorer: +-1 int8 query tiles and per-token constants
   bms::DeviceBuf cand_start, cand_end, cand_mask;  // candidate (rerank) mode: per-slot chunk ranges, valid-slot bitmask
   bms::DeviceBuf fde_simhash, fde_ams_index, fde_ams_sign, fde_tmp;  // FDE configuration (device copies) + scratch

@@ -64,7 +64,11 @@ template <typename T>
 __global__ void __launch_bounds__(kTopkThreads)
 topk_kernel(const T* __restrict__ gs, int64_t n_pages, int64_t ld, const int32_t* __restrict__ group_offsets,
             const uint32_t* __restrict__ allow, int k, float scale, int64_t id_base, const int64_t* __restrict__ id_map,
-            float* __restrict__ top_scores, int64_t* __restrict__ top_ids, int32_t* __restrict__ top_counts) {
+            float* __restrict__ top_scores, int64_t* __restrict__ top_ids, int32_t* __restrict__ top_counts,
+            int64_t slice_pages, uint32_t* __restrict__ part_keys, int64_t* __restrict__ part_ids) {
+  // grid = (n_q, n_slices): CTA (q, s) selects the exact top-k of pages [s*slice_pages, (s+1)*slice_pages).  With one slice
+  // it writes the final result; otherwise (raw key, id) candidates for topk_merge_kernel (global top-k is a subset of the
+  // union of the slices' top-k, and both levels order by (key DESC, id ASC), so the result is identical).
   extern __shared__ uint64_t win[];  // [n2] winners as (key << 32) | (0xffffffff - page)
   __shared__ uint32_t hist[256];
   __shared__ uint32_t s_prefix, s_need, s_total, s_gt, s_eq_base;
@@ -73,6 +77,8 @@ topk_kernel(const T* __restrict__ gs, int64_t n_pages, int64_t ld, const int32_t
   const int q = blockIdx.x;
   const int g0 = group_offsets[q], g1 = group_offsets[q + 1];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int64_t pbeg = int64_t(blockIdx.y) * slice_pages;
+  const int64_t pend = pbeg + slice_pages < n_pages ? pbeg + slice_pages : n_pages;
 
   // ---- radix select of the k-th largest key (4 x 8 bits, most significant first)
   uint32_t prefix = 0, need = 0, total = 0;
@@ -81,10 +87,25 @@ topk_kernel(const T* __restrict__ gs, int64_t n_pages, int64_t ld, const int32_t
     if (tid < 256) hist[tid] = 0;
     __syncthreads();
     const uint32_t hi_mask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
-    for (int64_t p = tid; p < n_pages; p += kTopkThreads) {
-      uint32_t key;
-      if (!page_key(gs, ld, g0, g1, allow, p, &key)) continue;
-      if ((key & hi_mask) == prefix) atomicAdd(&hist[(key >> shift) & 0xffu], 1u);
+    // Scores of one query usually share their leading bytes, so most pages fall into ONE bin: aggregate equal bins inside
+    // the warp first (__match_any_sync) -- one shared-memory atomic per distinct bin per warp instead of one per page.
+    // 4 pages per thread per trip, all loads issued before the first warp-synchronous step (a __match_any_sync between
+    // two dependent loads would expose the full L2/HBM latency on every trip).
+    for (int64_t base = pbeg; base < pend; base += 4 * kTopkThreads) {
+      uint32_t key[4];
+      bool in[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int64_t p = base + u * kTopkThreads + tid;
+        key[u] = 0;
+        in[u] = p < pend && page_key(gs, ld, g0, g1, allow, p, &key[u]) && (key[u] & hi_mask) == prefix;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t bin = in[u] ? ((key[u] >> shift) & 0xffu) : 0xffffffffu;
+        const uint32_t peers = __match_any_sync(0xffffffffu, bin);
+        if (in[u] && lane == __ffs(peers) - 1) atomicAdd(&hist[bin], uint32_t(__popc(peers)));
+      }
     }
     __syncthreads();
     if (tid == 0) {
@@ -126,10 +147,17 @@ topk_kernel(const T* __restrict__ gs, int64_t n_pages, int64_t ld, const int32_t
   // ---- collect: keys > thr anywhere, keys == thr in ascending page order until need_eq are taken
   if (kk > 0) {
     const uint32_t n_gt = kk - need_eq;
-    for (int64_t base = 0; base < n_pages; base += kTopkThreads) {
+    uint32_t nkey = 0;
+    bool nvalid = pbeg + tid < pend && page_key(gs, ld, g0, g1, allow, pbeg + tid, &nkey);
+    for (int64_t base = pbeg; base < pend; base += kTopkThreads) {
       const int64_t p = base + tid;
-      uint32_t key = 0;
-      const bool valid = p < n_pages && page_key(gs, ld, g0, g1, allow, p, &key);
+      const uint32_t key = nkey;
+      const bool valid = nvalid;
+      {  // software prefetch of the next chunk: its load overlaps the three block-wide barriers below
+        const int64_t pn = p + kTopkThreads;
+        nkey = 0;
+        nvalid = pn < pend && page_key(gs, ld, g0, g1, allow, pn, &nkey);
+      }
       const bool gt = valid && key > thr;
       const bool eq = valid && key == thr;
       if (gt) {
@@ -156,11 +184,18 @@ topk_kernel(const T* __restrict__ gs, int64_t n_pages, int64_t ld, const int32_t
   for (int i = tid; i < k; i += kTopkThreads) {
     const bool live = uint32_t(i) < kk;
     const uint64_t w = live ? win[i] : 0;
-    top_scores[int64_t(q) * k + i] = live ? score_of_key(uint32_t(w >> 32), T(0)) * scale : -CUDART_INF_F;
     const int64_t slot = int64_t(0xffffffffu - uint32_t(w));
-    top_ids[int64_t(q) * k + i] = live ? (id_map ? __ldg(id_map + slot) : slot + id_base) : int64_t(-1);
+    const int64_t id = live ? (id_map ? __ldg(id_map + slot) : slot + id_base) : int64_t(-1);
+    if (part_keys) {
+      const int64_t o = (int64_t(q) * gridDim.y + blockIdx.y) * k + i;
+      part_keys[o] = uint32_t(w >> 32);
+      part_ids[o] = id;
+    } else {
+      top_scores[int64_t(q) * k + i] = live ? score_of_key(uint32_t(w >> 32), T(0)) * scale : -CUDART_INF_F;
+      top_ids[int64_t(q) * k + i] = id;
+    }
   }
-  if (tid == 0) top_counts[q] = int32_t(kk);
+  if (tid == 0 && !part_keys) top_counts[q] = int32_t(kk);
 }
 
 // ------------------------------------------------------------------------------------------ merge of candidate lists
@@ -168,9 +203,13 @@ __device__ __forceinline__ bool cand_before(uint32_t ka, int64_t ia, uint32_t kb
   return ka > kb || (ka == kb && ia < ib);  // score DESC, id ASC; invalid entries carry key 0 / id INT64_MAX
 }
 
+// cand_keys != NULL: candidates carry raw order-preserving keys of score type T (second level of topk_kernel; exact for int
+// scores beyond 2^24 too); else float scores (merge of per-shard lists after the all-gather).
+template <typename T>
 __global__ void __launch_bounds__(1024)
-merge_topk_kernel(const float* __restrict__ cand_scores, const int64_t* __restrict__ cand_ids, int m, int n2, int k,
-                  float* __restrict__ top_scores, int64_t* __restrict__ top_ids, int32_t* __restrict__ top_counts) {
+merge_topk_kernel(const float* __restrict__ cand_scores, const uint32_t* __restrict__ cand_keys,
+                  const int64_t* __restrict__ cand_ids, int m, int n2, int k, float scale, float* __restrict__ top_scores,
+                  int64_t* __restrict__ top_ids, int32_t* __restrict__ top_counts) {
   extern __shared__ uint8_t msm[];
   int64_t* ids = reinterpret_cast<int64_t*>(msm);
   uint32_t* keys = reinterpret_cast<uint32_t*>(ids + n2);
@@ -181,13 +220,13 @@ merge_topk_kernel(const float* __restrict__ cand_scores, const int64_t* __restri
   uint32_t mine = 0;
   for (int i = threadIdx.x; i < n2; i += blockDim.x) {
     int64_t id = -1;
-    float s = 0.f;
+    uint32_t kraw = 0;
     if (i < m) {
       id = cand_ids[int64_t(q) * m + i];
-      s = cand_scores[int64_t(q) * m + i];
+      kraw = cand_keys ? cand_keys[int64_t(q) * m + i] : key_of(cand_scores[int64_t(q) * m + i]);
     }
     const bool ok = id >= 0;
-    keys[i] = ok ? key_of(s) : 0u;
+    keys[i] = ok ? kraw : 0u;
     ids[i] = ok ? id : INT64_MAX;
     mine += ok;
   }
@@ -215,10 +254,26 @@ merge_topk_kernel(const float* __restrict__ cand_scores, const int64_t* __restri
   const uint32_t kk = s_valid < uint32_t(k) ? s_valid : uint32_t(k);
   for (int i = threadIdx.x; i < k; i += blockDim.x) {
     const bool live = uint32_t(i) < kk;
-    top_scores[int64_t(q) * k + i] = live ? score_of_key(keys[i], 0.f) : -CUDART_INF_F;
+    top_scores[int64_t(q) * k + i] = live ? score_of_key(keys[i], T(0)) * scale : -CUDART_INF_F;
     top_ids[int64_t(q) * k + i] = live ? ids[i] : int64_t(-1);
   }
   if (threadIdx.x == 0) top_counts[q] = int32_t(kk);
+}
+
+template <typename T>
+static int launch_merge_impl(b200ms_t* h, const float* cand_scores, const uint32_t* cand_keys, const int64_t* cand_ids, int n_q,
+                             int m, int k, float scale, float* top_scores, int64_t* top_ids, int32_t* top_counts,
+                             cudaStream_t s) {
+  int n2 = 2;
+  while (n2 < m) n2 <<= 1;
+  const size_t smem = size_t(n2) * (sizeof(int64_t) + sizeof(uint32_t));
+  auto kern = merge_topk_kernel<T>;
+  if (int e = check_cuda(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)),
+                         "cudaFuncSetAttribute(merge_topk)"))
+    return e;
+  kern<<<n_q, 1024, smem, s>>>(cand_scores, cand_keys, cand_ids, m, n2, k, scale, top_scores, top_ids, top_counts);
+  h->launches++;
+  return check_cuda(h, cudaGetLastError(), "launch merge_topk");
 }
 
 int launch_topk(b200ms_t* h, const void* group_scores, int score_dtype, int64_t n_pages, int64_t ld,
@@ -229,31 +284,45 @@ int launch_topk(b200ms_t* h, const void* group_scores, int score_dtype, int64_t 
   int n2 = 1;
   while (n2 < k) n2 <<= 1;
   const size_t smem = size_t(n2) * sizeof(uint64_t);
+  // slices per query: enough CTAs to spread a big corpus over the SMs (one CTA sweeping 262144 pages took 0.87 ms),
+  // bounded by the merge kernel's 8192-candidate capacity
+  int64_t slices = n_pages / 8192;
+  const int64_t cap = (2 * B200MS_MAX_K) / k;
+  if (slices > cap) slices = cap;
+  if (slices > 64) slices = 64;
+  if (slices < 1) slices = 1;
+  const int64_t slice_pages = (n_pages + slices - 1) / slices;
+  uint32_t* part_keys = nullptr;
+  int64_t* part_ids = nullptr;
+  if (slices > 1) {
+    if (int e = reserve(h, h->topk_keys, size_t(n_q) * slices * k * 4)) return e;
+    if (int e = reserve(h, h->topk_ids, size_t(n_q) * slices * k * 8)) return e;
+    part_keys = static_cast<uint32_t*>(h->topk_keys.p);
+    part_ids = static_cast<int64_t*>(h->topk_ids.p);
+  }
+  const dim3 grid(n_q, unsigned(slices));
   if (score_dtype == B200MS_F32) {
-    topk_kernel<float><<<n_q, kTopkThreads, smem, s>>>(static_cast<const float*>(group_scores), n_pages, ld,
-                                                      group_offsets_dev, allow_mask, k, scale, id_base, id_map,
-                                                      top_scores, top_ids, top_counts);
+    topk_kernel<float><<<grid, kTopkThreads, smem, s>>>(static_cast<const float*>(group_scores), n_pages, ld,
+                                                       group_offsets_dev, allow_mask, k, scale, id_base, id_map, top_scores,
+                                                       top_ids, top_counts, slice_pages, part_keys, part_ids);
   } else {
-    topk_kernel<int><<<n_q, kTopkThreads, smem, s>>>(static_cast<const int*>(group_scores), n_pages, ld,
-                                                    group_offsets_dev, allow_mask, k, scale, id_base, id_map,
-                                                    top_scores, top_ids, top_counts);
+    topk_kernel<int><<<grid, kTopkThreads, smem, s>>>(static_cast<const int*>(group_scores), n_pages, ld, group_offsets_dev,
+                                                     allow_mask, k, scale, id_base, id_map, top_scores, top_ids, top_counts,
+                                                     slice_pages, part_keys, part_ids);
   }
   h->launches++;
-  return check_cuda(h, cudaGetLastError(), "launch topk");
+  if (int e = check_cuda(h, cudaGetLastError(), "launch topk")) return e;
+  if (slices == 1) return B200MS_OK;
+  const int m = int(slices) * k;
+  return score_dtype == B200MS_F32
+             ? launch_merge_impl<float>(h, nullptr, part_keys, part_ids, n_q, m, k, scale, top_scores, top_ids, top_counts, s)
+             : launch_merge_impl<int>(h, nullptr, part_keys, part_ids, n_q, m, k, scale, top_scores, top_ids, top_counts, s);
 }
 
 int launch_merge_topk(b200ms_t* h, const float* cand_scores, const int64_t* cand_ids, int n_q, int m, int k,
                       float* top_scores, int64_t* top_ids, int32_t* top_counts, cudaStream_t s) {
   if (n_q <= 0) return B200MS_OK;
-  int n2 = 2;
-  while (n2 < m) n2 <<= 1;
-  const size_t smem = size_t(n2) * (sizeof(int64_t) + sizeof(uint32_t));
-  if (int e = check_cuda(h, cudaFuncSetAttribute(merge_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)),
-                         "cudaFuncSetAttribute(merge_topk)"))
-    return e;
-  merge_topk_kernel<<<n_q, 1024, smem, s>>>(cand_scores, cand_ids, m, n2, k, top_scores, top_ids, top_counts);
-  h->launches++;
-  return check_cuda(h, cudaGetLastError(), "launch merge_topk");
+  return launch_merge_impl<float>(h, cand_scores, nullptr, cand_ids, n_q, m, k, 1.0f, top_scores, top_ids, top_counts, s);
 }
 
 }  // namespace bms

@@ -329,3 +329,37 @@ def test_properties_at_scale_bf16():
     for qi in range(32):
         _, oi = orc.topk_np(sb[qi].astype(np.float32), 10)
         assert ti[qi].tolist() == oi.tolist()
+
+
+@pytest.mark.parametrize("dtype", ["binary", "int8"])
+def test_sliced_topk_is_exact_with_ties_and_large_ints(dtype):
+    """Corpora above 16384 pages use the two-level top-k (per-slice select + raw-key merge): the result must equal the
+    oracle's global (score DESC, id ASC) order -- including exact ties (binary) and int scores above 2^24 (int8)."""
+    rng = np.random.default_rng(123)
+    n_pages = 40000
+    base = np.sign(rng.standard_normal((n_pages * 32, 128))).astype(np.float32)
+    base[base == 0] = 1.0
+    if dtype == "int8":
+        base *= rng.uniform(0.5, 1.0, size=(n_pages * 32, 1)).astype(np.float32)
+    # many duplicate pages -> exact ties spread over different slices
+    base[32 * 30000:32 * 30100] = base[32 * 100:32 * 200]
+    base[32 * 39900:32 * 40000] = base[32 * 100:32 * 200]
+    rows = torch.from_numpy(base).cuda()
+    idx = MaxSimIndex(dtype=dtype)
+    step = 5000
+    for p0 in range(0, n_pages, step):
+        idx.add_pages(list(rows[p0 * 32:(p0 + step) * 32].view(step, 32, 128)))
+    queries = [base[32 * 150:32 * 150 + 32].copy(), np.sign(rng.standard_normal((20, 128))).astype(np.float32)]
+    got = idx.score_matrix(queries)
+    for k in (10, 1000, 4096):
+        ts, ti, tc = idx.search_host(queries, k=k)
+        for qi in range(2):
+            os_, oi = orc.topk_np(got[qi], k)  # scores are exact integers / multiples of 1/128: ranking them is the oracle order
+            assert ti[qi].tolist() == oi.tolist(), (dtype, k, qi)
+    off = orc.page_offsets([32] * n_pages)
+    if dtype == "binary":
+        want, _ = orc.binary_maxsim_c(orc.sign_pack_c(queries[0]), orc.sign_pack_c(base), off)
+        assert np.array_equal(got[0], want)
+    else:
+        want = orc.int8_maxsim_c(orc.quantize_int8_np(queries[0], 127.0), orc.quantize_int8_np(base, 127.0), off)
+        assert np.array_equal(np.rint(got[0] * 127.0 * 127.0).astype(np.int64), want) and want.max() > (1 << 24)
