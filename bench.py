@@ -242,6 +242,10 @@ def run_gpu(args):
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     if world > 1:
+        # keep stdout to the ONE JSON line: with NCCL_DEBUG=VERSION or WARN (set by some images) NCCL prints
+        # "NCCL version ..." on stdout at communicator creation; unset it unless the user asked for INFO/TRACE
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
+            os.environ.pop("NCCL_DEBUG")
         dist.init_process_group("nccl", device_id=device)
     peaks = load_peaks()
     n_pages, n_q, k = args.pages, args.bq, args.k
