@@ -373,7 +373,7 @@ def run_gpu(args):
         sm1_avg = sum(sm1) / len(sm1)
         gbs = rows * DIM * 2 / (sm1_avg * 1e-3) / 1e9
         hbm = {"workload": f"same shard, ONE query x {T_TOK} tokens (B_q*T = 32: HBM-bound regime)", "bound": "hbm",
-               "kernel": "maxsim_umma_kernel<bf16,NM=1,S4>", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+               "kernel": "maxsim_umma_kernel<bf16,NM=1>", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                "frac": gbs / peaks["hbm_gbs"], "peak_kind": f"{peaks['source']} copy bandwidth",
                "patch_vectors_per_sec": rows / (sm1_avg * 1e-3), "score_ms": sm1_avg,
                "step_ms": e0.elapsed_time(e1) / args.steps,

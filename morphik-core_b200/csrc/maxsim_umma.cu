@@ -547,8 +547,10 @@ int launch_score_umma(b200ms_t* h, const UnitPlan* plan, const void* q_packed, i
   const int n_mtiles = n_groups_padded / 4;
   const int n_q_rows = n_groups_padded * kGroup;
   const bool ts = h->a_in_tmem != 0;
-  // Single 32-token group: replicated-query form (32-row TMA boxes).  Measured at 65536 pages: bf16 2.40 vs 2.51-2.59 ms
-  // (7.2 TB/s), but int8 1.65 vs 1.42 ms -- so split4 = 1 (default) enables it for bf16 only, 2 forces it for both.
+  // Single 32-token group: optional replicated-query form (32-row TMA boxes).  In short runs it is 5 % faster for bf16
+  // (2.40 vs 2.51-2.59 ms at 65536 pages) but it makes the tensor cores multiply four copies of real data instead of
+  // 96 zero rows, and under the sustained 1 kW power cap of bench.py that costs 7 % of HBM throughput (6.0 vs 6.5 TB/s,
+  // A/B on one box) -- so it is OFF by default (split4 = 0); 1 enables it for bf16, 2 for every dtype.
   if (!ts && n_groups_real == 1 && (h->split4 == 2 || (h->split4 == 1 && c.dtype == B200MS_BF16))) {
     if (int e = make_tmap_rows(h, &h->tmap_q, q_packed, c.dtype, int64_t(n_q_rows), 32)) return e;
     return c.dtype == B200MS_BF16
