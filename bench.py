@@ -295,7 +295,7 @@ def run_gpu(args):
     for _ in range(args.warmup):
         step_device()
     barrier()
-    launches0, calls0 = idx.launch_count(), int(idx_score_calls(idx))
+    launches0 = idx.launch_count()
     sampler = ClockSampler(local_rank)
     sampler.start()
     time.sleep(0.25)
@@ -404,12 +404,6 @@ def run_gpu(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-
-
-def idx_score_calls(idx):
-    from morphik_core_b200 import _native as nat
-
-    return nat.lib.b200ms_score_call_count(idx.h.ptr)
 
 
 def main():

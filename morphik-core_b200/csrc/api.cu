@@ -150,11 +150,12 @@ B200MS_API int b200ms_create(int device, b200ms_t** out) {
   if (const char* e = getenv("B200MS_A_IN_TMEM")) h->a_in_tmem = atoi(e) != 0;
   if (const char* e = getenv("B200MS_B1_TENSOR")) h->b1_tensor = atoi(e);
   if (const char* e = getenv("B200MS_SPLIT4")) h->split4 = atoi(e);
+  if (const char* e = getenv("B200MS_UNIT_ROWS")) { if (atoll(e) > 0) h->unit_rows = atoll(e); }
   if (int e = check_cuda(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking), "cudaStreamCreate")) {
     delete h;
     return e;
   }
-  for (int i = 0; i < b200ms::kEvRing; ++i) {
+  for (int i = 0; i < b200ms_t::kEvRing; ++i) {
     cudaEventCreate(&h->ev0[i]);
     cudaEventCreate(&h->ev1[i]);
   }
@@ -171,8 +172,7 @@ B200MS_API int b200ms_destroy(b200ms_t* h) {
                        &h->cand_mask, &h->topk_keys, &h->topk_ids, &h->b1_q_i8, &h->b1_tok_const, &h->fde_simhash, &h->fde_ams_index, &h->fde_ams_sign, &h->fde_tmp};
   for (DeviceBuf* b : bufs)
     if (b->p) cudaFree(b->p);
-  if (h->pinned) cudaFreeHost(h->pinned);
-  for (int i = 0; i < b200ms::kEvRing; ++i) {
+  for (int i = 0; i < b200ms_t::kEvRing; ++i) {
     if (h->ev0[i]) cudaEventDestroy(h->ev0[i]);
     if (h->ev1[i]) cudaEventDestroy(h->ev1[i]);
   }
@@ -378,7 +378,7 @@ static int score_impl(b200ms_t* h, const void* q_packed, int n_groups, const int
   if (n_groups < 0 || ld < n_items || n_cand < 0 || (n_groups > 0 && (!q_packed || !group_scores)))
     return set_error(h, B200MS_EINVAL, "score: bad arguments");
   if (n_groups == 0 || n_items == 0 || c.n_pages == 0) return B200MS_OK;
-  const int slot = int(h->ev_count % b200ms::kEvRing);
+  const int slot = int(h->ev_count % b200ms_t::kEvRing);
   const int n_groups_padded = (n_groups + 3) & ~3;
   if (c.dtype == B200MS_B1) {
     if (!q_lens || !group_offsets || n_q <= 0) return set_error(h, B200MS_EINVAL, "score: B1 needs q_lens and group_offsets");
@@ -441,7 +441,7 @@ B200MS_API int b200ms_score(b200ms_t* h, const void* q_packed, int n_groups, con
 }
 
 static int score_time_of(b200ms_t* h, int64_t idx, float* ms) {
-  const int slot = int(idx % b200ms::kEvRing);
+  const int slot = int(idx % b200ms_t::kEvRing);
   if (cudaEventSynchronize(h->ev1[slot]) != cudaSuccess) return check_cuda(h, cudaGetLastError(), "cudaEventSynchronize");
   if (cudaEventElapsedTime(ms, h->ev0[slot], h->ev1[slot]) != cudaSuccess) return check_cuda(h, cudaGetLastError(), "cudaEventElapsedTime");
   return B200MS_OK;
@@ -460,7 +460,7 @@ B200MS_API int64_t b200ms_score_call_count(const b200ms_t* h) { return h ? h->ev
 
 B200MS_API int b200ms_score_times_ms(b200ms_t* h, float* out_ms, int n) {
   if (!h || !out_ms || n < 0) return B200MS_EINVAL;
-  if (n > b200ms::kEvRing || n > h->ev_count) return set_error(h, B200MS_EINVAL, "score_times_ms: n exceeds the recorded history (ring of 256)");
+  if (n > b200ms_t::kEvRing || n > h->ev_count) return set_error(h, B200MS_EINVAL, "score_times_ms: n exceeds the recorded history (ring of 256)");
   DeviceGuard g(h->device);
   for (int i = 0; i < n; ++i)
     if (int e = score_time_of(h, h->ev_count - n + i, &out_ms[i])) return e;

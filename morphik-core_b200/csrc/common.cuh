@@ -62,8 +62,6 @@ struct b200ms {
   bms::DeviceBuf fde_simhash, fde_ams_index, fde_ams_sign, fde_tmp;  // FDE configuration (device copies) + scratch
   int fde_dim = 0, fde_reps = 0, fde_ksim = 0, fde_proj = 0;
   float fde_scale = 1.f;
-  void* pinned = nullptr;  // pinned host staging
-  size_t pinned_cap = 0;
   cudaStream_t stream = nullptr;  // internal stream for *_host entry points
   // ring of CUDA-event pairs bracketing the scoring kernels of the most recent b200ms_score / search calls
   static constexpr int kEvRing = 256;

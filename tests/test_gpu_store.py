@@ -153,3 +153,22 @@ def test_two_stage_store_matches_exhaustive_when_candidates_cover_corpus():
     a, b = run(ex.query_similar(q, k=8)), run(two.query_similar(q, k=8))
     assert [(r.document_id, r.chunk_number) for r in a] == [(r.document_id, r.chunk_number) for r in b]
     ex.close(); two.close()
+
+
+def test_concurrent_queries_are_serialised_and_consistent():
+    """Several query_similar coroutines in flight at once (the API server's situation, SURVEY 8b 'Threading'): the store's
+    lock serialises the GPU calls and every coroutine gets the answer of its own query."""
+    store = B200MultiVectorStore(mode="bf16")
+    rng = np.random.default_rng(21)
+    pages = [rng.standard_normal((int(rng.integers(10, 120)), 128)).astype(np.float32) for _ in range(200)]
+    run(store.store_embeddings([DocumentChunk(document_id=f"d{i}", content="", embedding=p, chunk_number=0) for i, p in enumerate(pages)]))
+    queries = [pages[i][:16] + 0.01 * rng.standard_normal((16, 128)).astype(np.float32) for i in range(24)]
+
+    async def many():
+        return await asyncio.gather(*[store.query_similar(q, k=3) for q in queries])
+
+    results = run(many())
+    assert [r[0].document_id for r in results] == [f"d{i}" for i in range(24)]
+    sequential = [run(store.query_similar(q, k=3)) for q in queries]
+    assert [[(c.document_id, c.score) for c in r] for r in results] == [[(c.document_id, c.score) for c in r] for r in sequential]
+    store.close()
