@@ -7,5 +7,9 @@ include/b200ms.h (ctypes).  Modules:
   models    DocumentChunk, the record type of core/models/chunk.py
   store     B200MultiVectorStore, the BaseVectorStore plugin (core/vector_store/base_vector_store.py:7-65)
   sharded   document-sharded multi-GPU search (torch.distributed / NCCL all-gather of per-shard top-k)
+  sharded_store  the BaseVectorStore plugin over all GPUs of a box (rank 0 serves, ranks > 0 run worker_loop)
+  fde       FixedDimensionalEncodingConfig / generate_*_encoding (MUVERA FDE) and TwoStageIndex (FDE candidates -> MaxSim rerank)
+  shardfile packed shard files (the HBM layout on disk) + importers for the reference's .npy / BIT(128)[] forms
+  reranker  embedding-based MaxSim reranker adapter
 """
 __version__ = "0.1.0"

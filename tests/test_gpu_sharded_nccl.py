@@ -80,3 +80,65 @@ def test_sharded_search_world2_nccl(tmp_path, mode):
         pytest.skip("needs 2 GPUs")
     mp.spawn(_worker, args=(2, _free_port(), mode, str(tmp_path)), nprocs=2, join=True)
     assert sorted(os.listdir(tmp_path)) == ["ok0", "ok1"]
+
+
+def _store_worker(rank, world, port, result_dir):
+    import asyncio
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from morphik_core_b200.models import DocumentChunk
+        from morphik_core_b200.sharded_store import ShardedB200MultiVectorStore
+        from oracle import maxsim_oracle as orc
+
+        store = ShardedB200MultiVectorStore(mode="bf16")
+        if rank != 0:
+            store.worker_loop()
+            open(os.path.join(result_dir, f"ok{rank}"), "w").write("ok")
+            return
+        run = asyncio.run
+        rng = np.random.default_rng(31)
+        docs = {}
+        for d in range(16):
+            pages = []
+            for _ in range(int(rng.integers(1, 6))):
+                x = rng.standard_normal((int(rng.integers(5, 300)), 128)).astype(np.float32)
+                pages.append(x / np.linalg.norm(x, axis=1, keepdims=True))
+            docs[f"doc{d}"] = pages
+            run(store.store_embeddings([DocumentChunk(document_id=f"doc{d}", content=f"{d}/{j}", embedding=p, chunk_number=j)
+                                        for j, p in enumerate(pages)]))
+        assert set(store.doc_rank.values()) == {0, 1}
+
+        def oracle(q, k, allowed=None):
+            flat = [(d, j, p) for d, ps in docs.items() for j, p in enumerate(ps) if allowed is None or d in allowed]
+            rows = orc.bf16_round_np(np.concatenate([p for _, _, p in flat]))
+            s = orc.float_maxsim_c(orc.bf16_round_np(q), rows, orc.page_offsets([len(p) for _, _, p in flat]))
+            order = np.argsort(-s.astype(np.float64), kind="stable")[:k]
+            return [(flat[i][0], flat[i][1]) for i in order], s[order]
+
+        q = rng.standard_normal((32, 128)).astype(np.float32)
+        res = run(store.query_similar(q, k=10))
+        want, ws = oracle(q, 10)
+        assert [(r.document_id, r.chunk_number) for r in res] == want
+        np.testing.assert_allclose([r.score for r in res], ws, rtol=3e-5)
+        on1 = [d for d, r in store.doc_rank.items() if r == 1][:3]
+        res = run(store.query_similar(q, k=50, doc_ids=on1))
+        assert [(r.document_id, r.chunk_number) for r in res] == oracle(q, 50, set(on1))[0]
+        for d in list(docs)[:7]:
+            run(store.delete_chunks_by_document_id(d))
+            docs.pop(d)
+        res = run(store.query_similar(q, k=10))
+        assert [(r.document_id, r.chunk_number) for r in res] == oracle(q, 10)[0]
+        store.close()
+        open(os.path.join(result_dir, "ok0"), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_store_world2_nccl(tmp_path):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    mp.spawn(_store_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    assert sorted(os.listdir(tmp_path)) == ["ok0", "ok1"]
