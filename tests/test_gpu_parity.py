@@ -363,3 +363,42 @@ def test_sliced_topk_is_exact_with_ties_and_large_ints(dtype):
     else:
         want = orc.int8_maxsim_c(orc.quantize_int8_np(queries[0], 127.0), orc.quantize_int8_np(base, 127.0), off)
         assert np.array_equal(np.rint(got[0] * 127.0 * 127.0).astype(np.int64), want) and want.max() > (1 << 24)
+
+
+@pytest.mark.parametrize("dtype", ["int8", "binary"])
+def test_properties_at_scale_int8_binary(dtype):
+    """16384 pages x 1024 patches (int8 2 GiB / 1-bit 256 MiB): invariants + oracle on a sample, single query and a batch
+    (the batch takes the tensor-core 1-bit path and the sliced top-k)."""
+    n_pages, p = 16384, 1024
+    g = torch.Generator(device="cuda").manual_seed(99)
+    rows = torch.nn.functional.normalize(torch.randn((n_pages * p, 128), generator=g, device="cuda"), dim=1)
+    q = torch.nn.functional.normalize(torch.randn((32, 128), generator=g, device="cuda"), dim=1)
+    rows[4242 * p: 4242 * p + 32] = q  # planted: contains the query tokens verbatim -> maximum score, rank 1
+    rows[9000 * p:9001 * p] = rows[5 * p:6 * p]  # duplicate page -> identical score
+    rows[43 * p:44 * p] = rows[42 * p:43 * p].flip(0)  # permuted rows -> identical score
+    idx = MaxSimIndex(dtype=dtype)
+    step = 2048
+    for p0 in range(0, n_pages, step):
+        idx.add_pages(list(rows[p0 * p:(p0 + step) * p].view(step, p, 128)))
+    qn = q.cpu().numpy()
+    others = [torch.nn.functional.normalize(torch.randn((32, 128), generator=g, device="cuda"), dim=1).cpu().numpy() for _ in range(7)]
+    s1 = idx.score_matrix([qn])[0]
+    sb = idx.score_matrix([qn] + others)
+    assert np.array_equal(sb[0], s1)  # same query alone (POPC / NM=1) and inside a batch (tensor path / NM=2): bit-identical
+    assert s1.argmax() == 4242 and s1[9000] == s1[5] and s1[43] == s1[42]
+    if dtype == "binary":
+        assert s1[4242] == 32.0  # every token finds itself: Hamming 0
+    sample = sorted(set(range(0, n_pages, 1024)) | {5, 42, 43, 4242, 9000})
+    rows_h = torch.stack([rows[i * p:(i + 1) * p].cpu() for i in sample]).numpy().reshape(-1, 128)
+    off = orc.page_offsets([p] * len(sample))
+    if dtype == "binary":
+        want = orc.binary_maxsim_c(orc.sign_pack_c(qn), orc.sign_pack_c(rows_h), off)[0]
+        assert np.array_equal(s1[sample], want)
+    else:
+        want = orc.int8_maxsim_c(orc.quantize_int8_np(qn, 127.0), orc.quantize_int8_np(rows_h, 127.0), off)
+        assert np.array_equal(np.rint(s1[sample] * 127.0 * 127.0).astype(np.int64), want)
+    ts, ti, tc = idx.search_host([qn] + others, k=10)
+    for qi in range(8):
+        _, oi = orc.topk_np(sb[qi], 10)
+        assert ti[qi].tolist() == oi.tolist()
+    assert ti[0][0] == 4242
