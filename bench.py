@@ -184,6 +184,46 @@ def cpu_reference_rate(n_q: int, budget_s: float, seed: int = 1234):
             "checksum": float(scores.sum())}
 
 
+def torch_gpu_reference_rate(rows_bf16, q_dev, n_q, sample_pages=4096, iters=5):
+    """The kernel-to-beat on the same GPU: the reference's OWN GPU formulation -- colpali_engine
+    score_multi_vector with device="cuda" (fast_multivector_store.py:339,553-555) = einsum("bnd,csd->bcns").max(3).sum(2)
+    over 128-page batches -- on a resident sample of the shard (no H2D), in bf16 and in fp32 (TF32 allowed, as the reference
+    enables it, colpali_embedding_model.py:32-35).  A reported baseline only; nothing here is on the product path."""
+    import torch
+
+    out = {}
+    pages = rows_bf16[: sample_pages * P_PATCH].view(sample_pages, P_PATCH, DIM)
+    q = q_dev.view(n_q, T_TOK, DIM)
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        for name, dt in (("bf16", torch.bfloat16), ("fp32_tf32", torch.float32)):
+            qq = q.to(dt)
+
+            def once():
+                acc = []
+                for j in range(0, sample_pages, 128):
+                    pb = pages[j:j + 128].to(dt)
+                    acc.append(torch.einsum("bnd,csd->bcns", qq, pb).max(dim=3)[0].sum(dim=2))
+                return torch.cat(acc, dim=1)
+
+            once()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(iters):
+                scores = once()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / iters
+            out[name] = {"value": sample_pages * P_PATCH / (ms * 1e-3), "unit": UNIT, "ms": ms,
+                         "checksum": float(scores.float().sum())}
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    out["sample"] = f"{sample_pages} resident pages x {P_PATCH} patches, {n_q} queries x {T_TOK} tokens, torch.einsum+max+sum, batch 128"
+    return out
+
+
 def run_reference(args):
     import torch
 
@@ -381,6 +421,14 @@ def run_gpu(args):
                "traffic": (tr["maxsim_umma<bf16,NM=1>"]["dram_bytes_per_patch_vector"] * rows
                            if tr and "maxsim_umma<bf16,NM=1>" in tr else None)}
 
+    # ---- the reference's own GPU formulation on the same GPU (rank 0, N=1 only)
+    torch_gpu = None
+    if rank == 0 and world == 1:
+        try:
+            torch_gpu = torch_gpu_reference_rate(packed.view(torch.bfloat16).view(-1, DIM), q_dev, n_q)
+        except Exception as e:  # noqa: BLE001  (a baseline must never break the bench line)
+            torch_gpu = {"error": repr(e)[:200]}
+
     # ---- CPU baseline beside it (rank 0, N=1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -398,6 +446,7 @@ def run_gpu(args):
                     "api": "b200ms_search_host (C-ABI, pinned host buffers)" if world == 1 else
                            "pinned H2D + ShardedMaxSim.search (NCCL all-gather + merge) + D2H"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "hbm_regime": hbm, "cpu_baseline": cpu,
+            "torch_gpu_reference_formulation": torch_gpu,
             "page_scores_per_sec": value / P_PATCH * n_q, "top1_sample": top1[:4],
         }
         print(json.dumps(line), flush=True)
