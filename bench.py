@@ -386,7 +386,7 @@ def run_gpu(args):
         traffic_bytes = tr["maxsim_umma<bf16,NM=4>"]["dram_bytes_per_patch_vector"] * rows  # per launch (one pass)
         traffic_src = tr["maxsim_umma<bf16,NM=4>"]["source"]
     roofline = {
-        "kernel": "maxsim_umma_kernel<bf16,NM=4>", "bound": "tensor", "achieved": achieved_tf,
+        "kernel": "maxsim_umma_w4_kernel<bf16,NM=4>", "bound": "tensor", "achieved": achieved_tf,
         "peak": peaks["tflops_sustained"], "unit": "TFLOP/s", "frac": achieved_tf / peaks["tflops_sustained"],
         "peak_kind": f"{peaks['source']} cuBLAS bf16 sustained (burst {peaks['tflops_burst']})",
         "frac_of_burst": achieved_tf / peaks["tflops_burst"], "traffic": traffic_bytes, "traffic_source": traffic_src,

@@ -475,6 +475,237 @@ maxsim_umma_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_c
   }
 }
 
+// ================================================================================================================
+// W4 form (NM = 4 for bf16, 4 or 8 for s8): FOUR epilogue warpgroups, warpgroup e owns TMEM accumulator e and the query
+// tiles m with m % 4 == e.  In the two-warpgroup form each warpgroup needs ~820 of the 1024 cycles it has per accumulator
+// (ncu: tensor pipe 73-76 % active although tcgen05.mma itself sustains 100 %, tools/umma_rate.cu); here every warpgroup
+// has 2048 cycles per accumulator and five warps per SM sub-partition hide the TMEM-load latency.  640 threads.
+constexpr int kThreadsW4 = 640;
+
+template <int KIND, int NM>
+__global__ void __launch_bounds__(kThreadsW4, 1)
+maxsim_umma_w4_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constant__ CUtensorMap tmap_q,
+                      const int32_t* __restrict__ chunk_page, const int32_t* __restrict__ unit_start,
+                      const int32_t* __restrict__ unit_end, int slot_mode, int n_units, int m_tile_base, int n_groups_real,
+                      typename Kind<KIND>::Acc* __restrict__ group_scores, int64_t ld, int num_stages) {
+  using K = Kind<KIND>;
+  using Acc = typename K::Acc;
+  static_assert(NM % 4 == 0, "W4 form needs a multiple of four query tiles");
+  constexpr int MPW = NM / 4;                  // query tiles per epilogue warpgroup
+  constexpr int kKSteps = KIND == 0 ? 8 : 4;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_q = smem;
+  uint8_t* smem_st = smem + NM * K::kTileBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_st + size_t(num_stages) * K::kTileBytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + 16;
+  uint64_t* tfull = bars + 32;
+  uint64_t* tempty = bars + 40;
+  uint64_t* qfull = bars + 48;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 56);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_rows);
+    prefetch_tmap(&tmap_q);
+    for (int i = 0; i < num_stages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < kNumAccum; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 4);
+    }
+    mbar_init(qfull, 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc_512(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint64_t pol_rows = policy_evict_first();
+      const uint64_t pol_q = policy_evict_last();
+      mbar_expect_tx(qfull, NM * K::kTileBytes);
+#pragma unroll
+      for (int m = 0; m < NM; ++m)
+#pragma unroll
+        for (int p = 0; p < K::kPanels; ++p)
+          tma_load_2d(&tmap_q, qfull, smem_q + m * K::kTileBytes + p * kSubtileBytes, p * K::kPanelElems,
+                      (m_tile_base + m) * kTileM, pol_q);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+        const int c0 = __ldg(unit_start + u), c1 = __ldg(unit_end + u);
+        const int n_tiles = (c1 - c0 + 3) >> 2;
+        for (int t = 0; t < n_tiles; ++t) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_expect_tx(&full[stage], K::kTileBytes);
+          uint8_t* dst = smem_st + size_t(stage) * K::kTileBytes;
+          const int row0 = (c0 + 4 * t) * kGroup;
+#pragma unroll
+          for (int p = 0; p < K::kPanels; ++p)
+            tma_load_2d(&tmap_rows, &full[stage], dst + p * kSubtileBytes, p * K::kPanelElems, row0, pol_rows);
+          if (++stage == num_stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = umma_idesc(KIND, kTileM, kTileN);
+    constexpr uint32_t kTileDesc = K::kTileBytes >> 4;
+    mbar_wait(qfull, 0);
+    tc_fence_after();
+    const uint64_t a_desc0 = umma_desc_kmajor_sw128(smem_u32(smem_q));
+    const uint64_t b_desc0 = umma_desc_kmajor_sw128(smem_u32(smem_st));
+    int stage = 0;
+    uint32_t phase = 0;
+    uint32_t use = 0;  // uses of every accumulator so far (each tile uses each buffer MPW times)
+    for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+      const int c0 = __ldg(unit_start + u), c1 = __ldg(unit_end + u);
+      const int n_tiles = (c1 - c0 + 3) >> 2;
+      for (int t = 0; t < n_tiles; ++t) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        const uint64_t bd = b_desc0 + uint64_t(uint32_t(stage) * kTileDesc);
+#pragma unroll 1
+        for (int m = 0; m < NM; ++m) {
+          const uint32_t buf = m & 3;
+          const uint32_t n = use + (m >> 2);
+          mbar_wait(&tempty[buf], (n & 1) ^ 1);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t d_tmem = tmem_base + buf * kTileN;
+            const uint64_t ad = a_desc0 + uint64_t(uint32_t(m) * kTileDesc);
+#pragma unroll
+            for (int ks = 0; ks < kKSteps; ++ks) {
+              const uint32_t off = ((ks >> 2) * kSubtileBytes + (ks & 3) * 32) >> 4;
+              umma_ss<KIND>(d_tmem, ad + off, bd + off, idesc, ks != 0);
+            }
+            umma_commit(&tfull[buf]);
+          }
+          __syncwarp();
+        }
+        use += MPW;
+        if (elect_one()) umma_commit(&empty[stage]);
+        __syncwarp();
+        if (++stage == num_stages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    const int wg = (warp - 4) >> 2;  // 0..3 = accumulator buffer owned
+    const int quad = warp & 3;
+    const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + wg * kTileN;
+    Acc runmax[MPW];
+    int cur_page[MPW];
+    uint32_t use = 0;
+    for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+      const int c0 = __ldg(unit_start + u), c1 = __ldg(unit_end + u);
+      const int n_tiles = (c1 - c0 + 3) >> 2;
+#pragma unroll
+      for (int i = 0; i < MPW; ++i) cur_page[i] = -1;
+      for (int t = 0; t < n_tiles; ++t) {
+        const int cb = c0 + 4 * t;
+        int pg[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) pg[j] = (cb + j < c1) ? __ldg(chunk_page + cb + j) : -1;
+#pragma unroll
+        for (int i = 0; i < MPW; ++i, ++use) {
+          const int m = wg + 4 * i;
+          const int group = (m_tile_base + m) * 4 + quad;
+          mbar_wait(&tfull[wg], use & 1);
+          tc_fence_after();
+          if (group < n_groups_real) {
+            uint32_t va[32], vb[32];
+            Acc cm[4];
+            tmem_ld_32x32(taddr, va);
+            tmem_ld_32x32(taddr + 32, vb);
+            tmem_ld_wait();
+            cm[0] = chunk_max<Acc>(va);
+            cm[1] = chunk_max<Acc>(vb);
+            tmem_ld_32x32(taddr + 64, va);
+            tmem_ld_32x32(taddr + 96, vb);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[wg]);
+            cm[2] = chunk_max<Acc>(va);
+            cm[3] = chunk_max<Acc>(vb);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if (pg[j] < 0) continue;
+              if (pg[j] != cur_page[i]) {
+                if (cur_page[i] >= 0) {
+                  const Acc s2 = warp_sum(runmax[i]);
+                  if (lane == 0) group_scores[int64_t(group) * ld + (slot_mode ? u : cur_page[i])] = s2;
+                }
+                cur_page[i] = pg[j];
+                runmax[i] = cm[j];
+              } else {
+                runmax[i] = acc_max(runmax[i], cm[j]);
+              }
+            }
+          } else {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[wg]);
+          }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < MPW; ++i) {
+        const int group = (m_tile_base + wg + 4 * i) * 4 + quad;
+        if (group < n_groups_real && cur_page[i] >= 0) {
+          const Acc s2 = warp_sum(runmax[i]);
+          if (lane == 0) group_scores[int64_t(group) * ld + (slot_mode ? u : cur_page[i])] = s2;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_512(tmem_base);
+  }
+}
+
+template <int KIND, int NM>
+static int launch_w4(b200ms_t* h, const UnitPlan& up, const CUtensorMap& tq, int m_tile_base, int n_groups_real,
+                     void* scores, int64_t ld, cudaStream_t s) {
+  using K = Kind<KIND>;
+  const Corpus& c = h->corpus;
+  const uint32_t avail = kSmemLimit - 1024 - kBarrierBytes - NM * K::kTileBytes;
+  int stages = int(avail / K::kTileBytes);
+  if (stages > 8) stages = 8;
+  if (stages < 2) return set_error(h, B200MS_EINVAL, "maxsim_umma_w4: not enough shared memory for 2 stages");
+  const uint32_t smem = 1024 + NM * K::kTileBytes + uint32_t(stages) * K::kTileBytes + kBarrierBytes;
+  auto kern = maxsim_umma_w4_kernel<KIND, NM>;
+  if (int e = check_cuda(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)),
+                         "cudaFuncSetAttribute(maxsim_umma_w4)"))
+    return e;
+  int grid = h->max_ctas > 0 ? h->max_ctas : h->num_sms;
+  if (grid > up.n_units) grid = up.n_units;
+  if (grid < 1) return B200MS_OK;
+  kern<<<grid, kThreadsW4, smem, s>>>(c.tmap, tq, static_cast<const int32_t*>(h->chunk_page.p), up.start, up.end, up.slot_mode,
+                                     up.n_units, m_tile_base, n_groups_real, static_cast<typename K::Acc*>(scores), ld, stages);
+  h->launches++;
+  return check_cuda(h, cudaGetLastError(), "launch maxsim_umma_w4");
+}
+
 // ---------------------------------------------------------------------------------------------- host side
 template <int KIND, int NM, bool AT, bool S4 = false>
 static int launch_one(b200ms_t* h, const UnitPlan& up, const CUtensorMap& tq, const void* q_rows, int n_q_rows,
@@ -513,6 +744,18 @@ static int launch_kind(b200ms_t* h, const UnitPlan& up, const CUtensorMap& tq, c
     int nm = 1;
     while (nm < rem && nm < kMaxNM) nm <<= 1;  // round up: a phantom (all-zero) tile beats a 2nd pass over the corpus
     int e;
+    if (!AT && h->epi_w4 && nm >= 4) {  // four-epilogue-warpgroup form
+      if (nm == 4) {
+        e = launch_w4<KIND, 4>(h, up, tq, base, n_groups_real, scores, ld, s);
+      } else if constexpr (KIND == 1) {
+        e = launch_w4<KIND, 8>(h, up, tq, base, n_groups_real, scores, ld, s);
+      } else {
+        e = set_error(h, B200MS_EINVAL, "maxsim_umma_w4: bad NM");
+      }
+      if (e) return e;
+      base += nm;
+      continue;
+    }
     switch (nm) {
       case 1: e = launch_one<KIND, 1, AT>(h, up, tq, q_rows, n_q_rows, base, n_groups_real, scores, ld, s); break;
       case 2: e = launch_one<KIND, 2, AT>(h, up, tq, q_rows, n_q_rows, base, n_groups_real, scores, ld, s); break;

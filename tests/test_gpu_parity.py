@@ -136,6 +136,19 @@ def test_bf16_ragged_pages_empty_pages_unit_boundaries(unit_rows_):
     assert np.all(got[:, [4, 12]] == 0.0)  # empty pages score exactly 0
 
 
+@pytest.mark.parametrize("dtype", ["bf16", "int8"])
+def test_w4_and_two_warpgroup_forms_agree(dtype):
+    """The four-epilogue-warpgroup kernel (default for >= 4 query tiles) and the two-warpgroup kernel are bit-identical."""
+    rng = np.random.default_rng(808)
+    lens = [1, 33, 0, 64, 700, 1030, 2] + list(rng.integers(1, 300, size=50))
+    pages = make_pages(rng, lens)
+    for n_q in (13, 32, 40):  # 4 tiles (bf16: NM=4; int8: NM=4), 8 tiles (int8: NM=8), 10 tiles (8 + phantom-padded 2)
+        queries = [unit_rows(rng, 32 if i % 2 else 29) for i in range(n_q)]
+        a = MaxSimIndex(dtype=dtype); a.set_option("epi_w4", 1); a.set_option("unit_rows", 400); a.add_pages(pages)
+        b = MaxSimIndex(dtype=dtype); b.set_option("epi_w4", 0); b.set_option("unit_rows", 400); b.add_pages(pages)
+        assert np.array_equal(a.score_matrix(queries), b.score_matrix(queries)), (dtype, n_q)
+
+
 @pytest.mark.parametrize("n_q,t", [(2, 32), (3, 32), (5, 17), (8, 32), (16, 32), (32, 32), (33, 20), (1, 70), (2, 1030)])
 def test_bf16_query_batches_and_long_queries(n_q, t):
     rng = np.random.default_rng(100 + n_q * 7 + t)
