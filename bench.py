@@ -379,14 +379,18 @@ def run_gpu(args):
     flops_per_step = 2.0 * rows * DIM * n_q * T_TOK
     achieved_tf = flops_per_step / (score_ms_avg * 1e-3) / 1e12
     n_mtiles = (n_q * T_TOK + 127) // 128
-    passes = (n_mtiles + 3) // 4
+    # default: CTA-pair kernel, 8 query tiles per pass; B200MS_PAIR_CTA=0 selects the one-CTA W4 kernel (4 tiles per pass)
+    pair = os.environ.get("B200MS_PAIR_CTA", "1") != "0" and n_mtiles >= 3
+    passes = (n_mtiles + 7) // 8 if pair else (n_mtiles + 3) // 4
+    kname, tkey = (("maxsim_umma_pair_kernel<bf16,NM=4>", "maxsim_umma_pair<bf16,NM=4>") if pair else
+                   ("maxsim_umma_w4_kernel<bf16,NM=4>", "maxsim_umma<bf16,NM=4>"))
     tr = load_traffic()
     traffic_bytes = traffic_src = None
-    if tr and "maxsim_umma<bf16,NM=4>" in tr:
-        traffic_bytes = tr["maxsim_umma<bf16,NM=4>"]["dram_bytes_per_patch_vector"] * rows  # per launch (one pass)
-        traffic_src = tr["maxsim_umma<bf16,NM=4>"]["source"]
+    if tr and tkey in tr:
+        traffic_bytes = tr[tkey]["dram_bytes_per_patch_vector"] * rows  # per launch (one pass)
+        traffic_src = tr[tkey]["source"]
     roofline = {
-        "kernel": "maxsim_umma_w4_kernel<bf16,NM=4>", "bound": "tensor", "achieved": achieved_tf,
+        "kernel": kname, "bound": "tensor", "achieved": achieved_tf,
         "peak": peaks["tflops_sustained"], "unit": "TFLOP/s", "frac": achieved_tf / peaks["tflops_sustained"],
         "peak_kind": f"{peaks['source']} cuBLAS bf16 sustained (burst {peaks['tflops_burst']})",
         "frac_of_burst": achieved_tf / peaks["tflops_burst"], "traffic": traffic_bytes, "traffic_source": traffic_src,

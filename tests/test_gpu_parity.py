@@ -138,15 +138,47 @@ def test_bf16_ragged_pages_empty_pages_unit_boundaries(unit_rows_):
 
 @pytest.mark.parametrize("dtype", ["bf16", "int8"])
 def test_w4_and_two_warpgroup_forms_agree(dtype):
-    """The four-epilogue-warpgroup kernel (default for >= 4 query tiles) and the two-warpgroup kernel are bit-identical."""
+    """The four-epilogue-warpgroup kernel and the two-warpgroup kernel (the one-CTA forms, pair_cta = 0) are bit-identical."""
     rng = np.random.default_rng(808)
     lens = [1, 33, 0, 64, 700, 1030, 2] + list(rng.integers(1, 300, size=50))
     pages = make_pages(rng, lens)
     for n_q in (13, 32, 40):  # 4 tiles (bf16: NM=4; int8: NM=4), 8 tiles (int8: NM=8), 10 tiles (8 + phantom-padded 2)
         queries = [unit_rows(rng, 32 if i % 2 else 29) for i in range(n_q)]
-        a = MaxSimIndex(dtype=dtype); a.set_option("epi_w4", 1); a.set_option("unit_rows", 400); a.add_pages(pages)
-        b = MaxSimIndex(dtype=dtype); b.set_option("epi_w4", 0); b.set_option("unit_rows", 400); b.add_pages(pages)
+        a = MaxSimIndex(dtype=dtype); a.set_option("epi_w4", 1); b = MaxSimIndex(dtype=dtype); b.set_option("epi_w4", 0)
+        for i_ in (a, b):
+            i_.set_option("pair_cta", 0); i_.set_option("unit_rows", 400); i_.add_pages(pages)
         assert np.array_equal(a.score_matrix(queries), b.score_matrix(queries)), (dtype, n_q)
+
+
+@pytest.mark.parametrize("dtype", ["bf16", "int8"])
+@pytest.mark.parametrize("unit_rows_,n_pages", [(400, 57), (64, 9), (4096, 3), (400, 1)])
+def test_cta_pair_form_agrees(dtype, unit_rows_, n_pages):
+    """The CTA-pair kernel (tcgen05 cta_group::2, two unit streams per pair) is bit-identical to the one-CTA kernels:
+    odd/even unit counts, fewer units than CTAs, a single page, phantom query tiles, int8 with NM = 8."""
+    rng = np.random.default_rng(909 + n_pages)
+    lens = ([1, 33, 0, 64, 700, 1030, 2] + list(rng.integers(1, 300, size=50)))[:n_pages]
+    pages = make_pages(rng, lens)
+    for n_q in (9, 13, 32, 40, 70):  # 3, 4, 8, 10, 18 query tiles
+        queries = [unit_rows(rng, 32 if i % 2 else 29) for i in range(n_q)]
+        a = MaxSimIndex(dtype=dtype); a.set_option("pair_cta", 1); a.set_option("unit_rows", unit_rows_); a.add_pages(pages)
+        b = MaxSimIndex(dtype=dtype); b.set_option("pair_cta", 0); b.set_option("unit_rows", unit_rows_); b.add_pages(pages)
+        ga, gb = a.score_matrix(queries), b.score_matrix(queries)
+        assert np.array_equal(ga, gb), (dtype, n_q, np.abs(ga - gb).max())
+        if dtype == "bf16" and n_q == 13:
+            assert_close_rel(ga, oracle_float(queries, pages), 3e-5)
+
+
+def test_cta_pair_form_large_and_topk():
+    """Pair kernel on a corpus that gives every pair many units (persistent loop, stage ring wrap, dummy tail tiles)."""
+    rng = np.random.default_rng(4242)
+    lens = list(rng.integers(900, 1100, size=700))
+    pages = make_pages(rng, lens)
+    queries = [unit_rows(rng, 32) for _ in range(32)]
+    a = MaxSimIndex(dtype="bf16"); a.set_option("pair_cta", 1); a.add_pages(pages)
+    b = MaxSimIndex(dtype="bf16"); b.set_option("pair_cta", 0); b.add_pages(pages)
+    assert np.array_equal(a.score_matrix(queries), b.score_matrix(queries))
+    ta, tb = a.search_host(queries, k=10), b.search_host(queries, k=10)
+    assert np.array_equal(ta[1], tb[1]) and np.array_equal(ta[0], tb[0])
 
 
 @pytest.mark.parametrize("n_q,t", [(2, 32), (3, 32), (5, 17), (8, 32), (16, 32), (32, 32), (33, 20), (1, 70), (2, 1030)])
