@@ -31,6 +31,13 @@ def _load() -> ctypes.CDLL:
             f"{LIB_PATH} is missing: build it with `python __graft_entry__.py build` "
             "(nvcc, sm_100a). morphik-core_b200 has no CPU fallback."
         )
+    from . import build_native
+
+    if build_native.mismatched():  # a library built from older sources would silently run old kernels
+        raise ImportError(
+            f"{LIB_PATH} does not match morphik-core_b200/csrc (source hash differs): rebuild it with "
+            "`python __graft_entry__.py build`."
+        )
     lib = ctypes.CDLL(LIB_PATH)
     vp, i32p, i64p, u32p, f32p = c_void_p, POINTER(c_int32), POINTER(c_int64), POINTER(c_uint32), POINTER(c_float)
     sig = {

@@ -26,12 +26,36 @@ def _nvcc() -> str:
     return "nvcc"
 
 
+STAMP = LIB + ".srchash"
+
+
+def source_hash() -> str:
+    """sha256 over the CUDA sources, headers and compiler flags: the identity of what libb200ms.so was built from."""
+    import hashlib
+
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    for rel in SOURCES + HEADERS:
+        h.update(rel.encode())
+        with open(os.path.join(CSRC, rel), "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
 def stale() -> bool:
-    if not os.path.exists(LIB):
+    """True when the library is missing or was built from different sources (content hash, so it also works on a copy of
+    the tree whose mtimes are meaningless)."""
+    if not (os.path.exists(LIB) and os.path.exists(STAMP)):
         return True
-    t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS] + [os.path.abspath(__file__)]
-    return any(os.path.getmtime(d) > t for d in deps)
+    with open(STAMP) as f:
+        return f.read().strip() != source_hash()
+
+
+def mismatched() -> bool:
+    """True only when a stamp exists and names different sources (a library without a stamp cannot be judged)."""
+    if not (os.path.exists(LIB) and os.path.exists(STAMP)):
+        return False
+    with open(STAMP) as f:
+        return f.read().strip() != source_hash()
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -59,6 +83,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError("nvcc failed; see output above")
     link = [_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs
     subprocess.run(link, check=True)
+    with open(STAMP, "w") as f:
+        f.write(source_hash() + "\n")
     return LIB
 
 
