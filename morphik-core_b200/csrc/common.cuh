@@ -74,6 +74,7 @@ struct b200ms {
   int split4 = 0;     // 0 (default): plain epilogue; 1: replicated-query form for bf16 single-group scans; 2: all dtypes
   int epi_w4 = 1;     // 1: NM >= 4 launches use the four-epilogue-warpgroup kernel (maxsim_umma_w4_kernel)
   int pair_cta = 1;   // 1 (default): passes with >= 3 query tiles use the CTA-pair kernel (cta_group::2, maxsim_umma_pair.cu)
+  int pair_clusters = -1;  // co-resident CTA pairs the device reports for the pair kernel (-1: not queried yet)
   int a_in_tmem = 0;  // 1: feed the query operand of tcgen05.mma from TMEM (TS form), 0: from shared memory (SS form)
   CUtensorMap tmap_q;  // rebuilt per score call
 };
@@ -89,6 +90,7 @@ int make_tmap_rows(b200ms_t* h, CUtensorMap* out, const void* base, int dtype, i
 // kernel launchers (each returns a b200ms error code and bumps h->launches)
 int launch_score_umma(b200ms_t* h, const UnitPlan* plan, const void* q_packed, int n_groups_real, void* group_scores,
                       int64_t ld, cudaStream_t s);
+constexpr int B200MS_EUNSUPPORTED_PAIR = -100;  // internal: pair kernel cannot be scheduled on this device
 int launch_score_umma_pair(b200ms_t* h, const UnitPlan& up, const CUtensorMap& tq, int nm, int m_tile_base,
                            int n_groups_real, void* scores, int64_t ld, cudaStream_t s);
 int launch_score_b1(b200ms_t* h, const int64_t* cand_ids, int64_t n_cand, const void* q_packed, int n_groups,

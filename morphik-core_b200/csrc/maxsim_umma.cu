@@ -713,9 +713,13 @@ static int launch_kind(b200ms_t* h, const UnitPlan& up, const CUtensorMap& tq, c
     if (!AT && h->pair_cta && rem >= 3) {  // CTA-pair form: 2*per query tiles in one pass over the corpus
       int per = 2;
       while (2 * per < rem && per < kMaxNM) per <<= 1;
-      if (int e2 = launch_score_umma_pair(h, up, tq, per, base, n_groups_real, scores, ld, s)) return e2;
-      base += 2 * per;
-      continue;
+      const int e2 = launch_score_umma_pair(h, up, tq, per, base, n_groups_real, scores, ld, s);
+      if (e2 == B200MS_OK) {
+        base += 2 * per;
+        continue;
+      }
+      if (e2 != B200MS_EUNSUPPORTED_PAIR) return e2;
+      h->pair_cta = 0;  // e.g. a partition without whole TPCs: the one-CTA kernels below do the same work
     }
     if (!AT && h->epi_w4 && nm >= 4) {  // four-epilogue-warpgroup form
       if (nm == 4) {

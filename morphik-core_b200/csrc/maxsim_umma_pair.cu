@@ -282,6 +282,17 @@ static int launch_pair(b200ms_t* h, const UnitPlan& up, const CUtensorMap& tq, i
     return e;
   if (up.n_units < 1) return B200MS_OK;
   int grid = (h->max_ctas > 0 ? h->max_ctas : h->num_sms) & ~1;  // whole pairs
+  if (h->pair_clusters < 0) {  // once per handle: can this device co-schedule CTA pairs of this size at all?
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2);
+    cfg.blockDim = dim3(kThreadsPair);
+    cfg.dynamicSmemBytes = smem;
+    int n = 0;
+    const cudaError_t qe = cudaOccupancyMaxActiveClusters(&n, kern, &cfg);
+    if (qe != cudaSuccess) (void)cudaGetLastError();
+    h->pair_clusters = qe == cudaSuccess ? n : 0;
+  }
+  if (h->pair_clusters < 1) return B200MS_EUNSUPPORTED_PAIR;  // caller falls back to the one-CTA kernels (still CUDA)
   const int want = (up.n_units + 1) & ~1;
   if (grid > want) grid = want;
   if (grid < 2) grid = 2;

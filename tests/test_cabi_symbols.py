@@ -87,3 +87,17 @@ def test_sass_has_blackwell_tensor_and_tma_instructions():
     for mnemonic in ("UTCHMMA", "UTCIMMA", "LDTM", "UTMALDG", "FMNMX3", "POPC"):
         assert mnemonic in sass, mnemonic
     assert "HMMA.16816" not in sass  # no legacy mma.sync path
+
+
+def test_library_matches_sources_and_stale_library_is_detected(tmp_path, monkeypatch):
+    """libb200ms.so carries a stamp of the sources it was built from; a mismatch must be detected (the loader then refuses
+    the library instead of silently running kernels from older sources)."""
+    from morphik_core_b200 import build_native as bn
+
+    assert os.path.exists(bn.STAMP) and not bn.stale() and not bn.mismatched()
+    fake = tmp_path / "libb200ms.so.srchash"
+    fake.write_text("0" * 64 + "\n")
+    monkeypatch.setattr(bn, "STAMP", str(fake))
+    assert bn.stale() and bn.mismatched()
+    monkeypatch.setattr(bn, "STAMP", str(tmp_path / "absent"))
+    assert bn.stale() and not bn.mismatched()  # no stamp: rebuild wanted, but the library cannot be called wrong
