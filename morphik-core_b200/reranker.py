@@ -8,7 +8,7 @@ query's multivector: "retrieve with any store, rerank with ColPali MaxSim on the
 """
 from __future__ import annotations
 
-from typing import List, Sequence, Union
+from typing import List, Optional, Sequence, Union
 
 import numpy as np
 
@@ -29,14 +29,19 @@ class B200MaxSimReranker:
         finally:
             idx.close()
 
-    async def rerank(self, query_embedding, chunks: List[DocumentChunk]) -> List[DocumentChunk]:
-        """Chunks must carry their multivector in ``embedding``; returns them sorted by MaxSim score (descending, stable)."""
+    async def rerank(self, query_embedding, chunks: List[DocumentChunk], min_score: Optional[float] = None
+                     ) -> List[DocumentChunk]:
+        """Chunks must carry their multivector in ``embedding``; returns them sorted by MaxSim score (descending, stable).
+        ``min_score`` (optional) drops chunks scoring below it -- the threshold retrieve_chunks accepts but never applies
+        (document_service.py:381-383)."""
         if not chunks:
             return []
         scores = self._scores(query_embedding, [c.embedding for c in chunks])
         order = sorted(range(len(chunks)), key=lambda i: (-scores[i], i))
         out = []
         for i in order:
+            if min_score is not None and scores[i] < min_score:
+                break
             c = chunks[i].model_copy() if hasattr(chunks[i], "model_copy") else chunks[i]
             c.score = float(scores[i])
             out.append(c)

@@ -80,6 +80,26 @@ def as_query_matrix(query_embedding) -> np.ndarray:
     return np.ascontiguousarray(q)
 
 
+def as_page_matrix(embedding):
+    """Page embedding -> [P,128] matrix for ``add_pages``.
+
+    CUDA torch tensors (what ColpaliEmbeddingModel holds before its ``.to(float32).numpy(force=True)``,
+    colpali_embedding_model.py:262,291) stay on the device as bf16/float32 and go straight into the pack kernel -- the
+    ingest fast path: no fp32 host copy, no Rust pack, no ``Bit`` objects, no ``executemany``
+    (multi_vector_store.py:681-703).  Everything else becomes a host float32 array, as the reference does (:334-337)."""
+    if hasattr(embedding, "detach"):
+        t = embedding.detach()
+        if t.is_cuda:
+            import torch
+
+            if t.dtype not in (torch.bfloat16, torch.float32):
+                t = t.float()
+            return t[None, :] if t.ndim == 1 else t
+        embedding = t.float().cpu().numpy()
+    emb = np.asarray(embedding, dtype=np.float32)
+    return emb[None, :] if emb.ndim == 1 else emb
+
+
 class B200MultiVectorStore(BaseVectorStore):
     """Exhaustive ColPali MaxSim store on one B200 (see module docstring)."""
 
@@ -133,12 +153,9 @@ class B200MultiVectorStore(BaseVectorStore):
             if getattr(c, "embedding", None) is None:
                 logger.error("Missing embeddings for chunk %s-%s", c.document_id, c.chunk_number)
                 continue
-            emb = np.asarray(c.embedding.detach().float().cpu().numpy() if hasattr(c.embedding, "detach") else c.embedding,
-                             dtype=np.float32)
-            if emb.ndim == 1:
-                emb = emb[None, :]
+            emb = as_page_matrix(c.embedding)
             if emb.ndim != 2 or emb.shape[1] != 128:
-                raise ValueError(f"chunk {c.document_id}-{c.chunk_number}: embedding must be [P,128], got {emb.shape}")
+                raise ValueError(f"chunk {c.document_id}-{c.chunk_number}: embedding must be [P,128], got {tuple(emb.shape)}")
             valid.append((c, emb))
         if not valid:
             self._last_store_metrics = build_store_metrics()
@@ -166,9 +183,12 @@ class B200MultiVectorStore(BaseVectorStore):
         return results[0]
 
     async def query_similar_batch(self, query_embeddings: Sequence[Any], k: int, doc_ids: Optional[List[str]] = None,
-                                  app_id: Optional[str] = None, skip_image_content: bool = False
-                                  ) -> List[List[DocumentChunk]]:
-        """Batched form (extension): one corpus pass scores every query of the batch."""
+                                  app_id: Optional[str] = None, skip_image_content: bool = False,
+                                  min_score: Optional[float] = None) -> List[List[DocumentChunk]]:
+        """Batched form (extension): one corpus pass scores every query of the batch.
+
+        ``min_score`` drops hits scoring below it (the reference accepts ``min_score`` in retrieve_chunks but never applies
+        it, document_service.py:381-383) -- scores are MaxSim sums, so the threshold is on that scale."""
         t0 = time.perf_counter()
         queries = [as_query_matrix(q) for q in query_embeddings]
         if len(self.catalog) == 0 or k <= 0:
@@ -185,6 +205,8 @@ class B200MultiVectorStore(BaseVectorStore):
         for qi in range(len(queries)):
             hits = []
             for j in range(int(tc[qi])):
+                if min_score is not None and float(ts[qi, j]) < min_score:
+                    break  # sorted by score descending
                 rec = self.catalog.records[int(ti[qi, j])]
                 hits.append(DocumentChunk(document_id=rec.document_id, chunk_number=rec.chunk_number, content=rec.content,
                                           embedding=[], metadata=dict(rec.metadata), score=float(ts[qi, j])))

@@ -84,6 +84,8 @@ def test_maxsim_reranker_adapter():
     assert [c.chunk_number for c in out] == np.argsort(-want, kind="stable").tolist() and out[0].chunk_number == 2
     np.testing.assert_allclose([c.score for c in out], np.sort(want)[::-1], rtol=3e-5)
     assert asyncio.run(rr.rerank(q, [])) == []
+    kept = asyncio.run(rr.rerank(q, chunks, min_score=float(np.sort(want)[-2]) - 1e-3))  # threshold just under the 2nd best
+    assert [c.chunk_number for c in kept] == [c.chunk_number for c in out[:2]]
     one = asyncio.run(rr.compute_score(q, embs[1]))
     many = asyncio.run(rr.compute_score(q, embs))
     assert abs(one - want[1]) < 1e-4 and np.allclose(many, want, rtol=3e-5)

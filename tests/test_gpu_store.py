@@ -117,6 +117,27 @@ def test_binary_scores_equal_sql_max_sim_oracle():
     store.close()
 
 
+@pytest.mark.parametrize("mode", ["bf16", "binary", "int8"])
+def test_device_tensor_ingest_fast_path_matches_host_ingest(mode):
+    """CUDA bf16 tensors (what the embedding model holds) go straight into the pack kernel; the stored corpus
+    and every score equal the reference-style host float32 ingest of the same bf16 values; min_score cuts the list."""
+    g = torch.Generator().manual_seed(5)
+    pages = [torch.nn.functional.normalize(torch.randn((n, 128), generator=g), dim=1).bfloat16() for n in (40, 1, 97, 1030, 33)]
+    q = torch.nn.functional.normalize(torch.randn((32, 128), generator=g), dim=1).bfloat16()
+    dev, host = B200MultiVectorStore(mode=mode), B200MultiVectorStore(mode=mode)
+    mk = lambda conv: [DocumentChunk(document_id=f"d{i}", content="", embedding=conv(p), chunk_number=0)  # noqa: E731
+                       for i, p in enumerate(pages)]
+    ok, ids, _ = run(dev.store_embeddings(mk(lambda p: p.cuda())))
+    assert ok and len(ids) == 5
+    run(host.store_embeddings(mk(lambda p: p.float().numpy())))
+    a, b = run(dev.query_similar(q.cuda(), k=5)), run(host.query_similar(q.float().numpy(), k=5))
+    assert [(r.document_id, r.score) for r in a] == [(r.document_id, r.score) for r in b]
+    cut = (a[1].score + a[2].score) / 2
+    c = run(dev.query_similar_batch([q], k=5, min_score=cut))[0]
+    assert [(r.document_id, r.score) for r in c] == [(r.document_id, r.score) for r in a[:2]]
+    dev.close(); host.close()
+
+
 def test_save_load_round_trip(tmp_path):
     store = B200MultiVectorStore(mode="bf16")
     rng = np.random.default_rng(8)

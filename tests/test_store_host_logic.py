@@ -5,6 +5,7 @@ import asyncio
 
 import numpy as np
 import pytest
+import torch
 
 from morphik_core_b200.catalog import PageCatalog, PageRecord
 from morphik_core_b200.models import DocumentChunk
@@ -114,3 +115,18 @@ def test_store_contract_matches_reference_tests():
     # batched extension returns one list per query, k larger than the corpus is fine
     out = run(store.query_similar_batch([np.array([qe]), np.array([-qe])], k=10))
     assert [len(o) for o in out] == [2, 2] and out[1][0].document_id == "similarity_test_2"
+    # min_score (accepted but ignored by the reference, document_service.py:381-383) cuts the sorted list
+    out = run(store.query_similar_batch([np.array([qe])], k=10, min_score=0.5))
+    assert [r.document_id for r in out[0]] == ["meta_doc"]
+    assert run(store.query_similar_batch([np.array([qe])], k=10, min_score=2.0)) == [[]]
+
+
+def test_as_page_matrix_host_forms():
+    from morphik_core_b200.store import as_page_matrix
+
+    a = as_page_matrix([[0.5] * 128, [1.0] * 128])
+    assert a.dtype == np.float32 and a.shape == (2, 128)
+    assert as_page_matrix(np.ones(128, dtype=np.float64)).shape == (1, 128)
+    t = torch.ones((3, 128), dtype=torch.bfloat16)  # CPU tensor: host float32, like the reference (multi_vector_store.py:334-337)
+    b = as_page_matrix(t)
+    assert isinstance(b, np.ndarray) and b.dtype == np.float32 and b.shape == (3, 128)
