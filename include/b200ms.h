@@ -186,8 +186,8 @@ int b200ms_set_tuning(b200ms_t* h, int64_t unit_rows, int max_ctas);
 /* Named options: "a_in_tmem" (0 = query operand of tcgen05.mma from shared memory, 1 = from TMEM), "b1_tensor" (1 = score
  * 1-bit corpora on tcgen05 with in-kernel bit expansion, 0 = POPC kernel, 2 = auto by query-group count), "split4" (replicated-
  * query epilogue for single-group scans: 0 off (default), 1 = bf16 only, 2 = all dtypes), "epi_w4" (1 = four-epilogue-warpgroup
- * kernel for batches of >= 4 query tiles, default), "pair_cta" (1 = passes with >= 3 query tiles run on CTA pairs with
- * tcgen05 cta_group::2, M = N = 256), "unit_rows", "max_ctas".  Changing unit_rows needs a new b200ms_set_corpus to take effect. */
+ * kernel for batches of >= 4 query tiles, default), "pair_cta" (CTA pairs with tcgen05 cta_group::2, M = N = 256:
+ * 0 = off, 1 = passes of >= 3 query tiles, 2 = also exactly 2 tiles (default)), "unit_rows", "max_ctas".  Changing unit_rows needs a new b200ms_set_corpus to take effect. */
 int b200ms_set_option(b200ms_t* h, const char* name, int64_t value);
 
 #ifdef __cplusplus

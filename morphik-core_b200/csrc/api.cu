@@ -151,7 +151,7 @@ B200MS_API int b200ms_create(int device, b200ms_t** out) {
   if (const char* e = getenv("B200MS_B1_TENSOR")) h->b1_tensor = atoi(e);
   if (const char* e = getenv("B200MS_SPLIT4")) h->split4 = atoi(e);
   if (const char* e = getenv("B200MS_EPI_W4")) h->epi_w4 = atoi(e) != 0;
-  if (const char* e = getenv("B200MS_PAIR_CTA")) h->pair_cta = atoi(e) != 0;
+  if (const char* e = getenv("B200MS_PAIR_CTA")) h->pair_cta = atoi(e);
   if (const char* e = getenv("B200MS_UNIT_ROWS")) { if (atoll(e) > 0) h->unit_rows = atoll(e); }
   if (int e = check_cuda(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking), "cudaStreamCreate")) {
     delete h;
@@ -224,7 +224,7 @@ B200MS_API int b200ms_set_option(b200ms_t* h, const char* name, int64_t value) {
   } else if (n == "epi_w4") {
     h->epi_w4 = value != 0;
   } else if (n == "pair_cta") {
-    h->pair_cta = value != 0;
+    h->pair_cta = int(value);
   } else if (n == "split4" && value >= 0 && value <= 2) {
     h->split4 = int(value);
   } else if (n == "b1_tensor" && value >= 0 && value <= 2) {

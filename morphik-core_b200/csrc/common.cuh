@@ -73,7 +73,7 @@ struct b200ms {
   int b1_tensor = 2;  // 1-bit corpora: 0 = POPC kernel, 1 = tcgen05 kernel (bits expanded to {0,1} int8 in smem), 2 = auto
   int split4 = 0;     // 0 (default): plain epilogue; 1: replicated-query form for bf16 single-group scans; 2: all dtypes
   int epi_w4 = 1;     // 1: NM >= 4 launches use the four-epilogue-warpgroup kernel (maxsim_umma_w4_kernel)
-  int pair_cta = 1;   // 1 (default): passes with >= 3 query tiles use the CTA-pair kernel (cta_group::2, maxsim_umma_pair.cu)
+  int pair_cta = 2;   // CTA-pair kernels (cta_group::2, maxsim_umma_pair.cu): 0 off, 1 for passes of >= 3 query tiles, 2 (default) also for 2 tiles
   int pair_clusters = -1;  // co-resident CTA pairs the device reports for the pair kernel (-1: not queried yet)
   int a_in_tmem = 0;  // 1: feed the query operand of tcgen05.mma from TMEM (TS form), 0: from shared memory (SS form)
   CUtensorMap tmap_q;  // rebuilt per score call

@@ -710,16 +710,22 @@ static int launch_kind(b200ms_t* h, const UnitPlan& up, const CUtensorMap& tq, c
     int nm = 1;
     while (nm < rem && nm < kMaxNM) nm <<= 1;  // round up: a phantom (all-zero) tile beats a 2nd pass over the corpus
     int e;
-    if (!AT && h->pair_cta && rem >= 3) {  // CTA-pair form: 2*per query tiles in one pass over the corpus
-      int per = 2;
-      while (2 * per < rem && per < kMaxNM) per <<= 1;
-      const int e2 = launch_score_umma_pair(h, up, tq, per, base, n_groups_real, scores, ld, s);
-      if (e2 == B200MS_OK) {
-        base += 2 * per;
-        continue;
+    if (!AT && h->pair_cta && rem >= (h->pair_cta >= 2 ? 2 : 3)) {
+      // CTA-pair forms: 2*per query tiles per pass.  Pick the largest per whose phantom (zero) tiles stay below a quarter
+      // of the pass -- 5 tiles run as 4 + 1, not as 8 (measured per pass at 32768 pages: 8 tiles 5.08 ms, 4 tiles ~2.5 ms,
+      // one tile 1.28 ms); pair_cta = 2 also sends exactly two tiles to the two-tile pair kernel.
+      int per = kMaxNM;
+      while (per > 1 && rem < 2 * per - (per >= 4 ? per / 4 : 1)) per >>= 1;
+      if (per == 1 && (h->pair_cta < 2 || rem < 2)) per = 0;
+      if (per > 0) {
+        const int e2 = launch_score_umma_pair(h, up, tq, per, base, n_groups_real, scores, ld, s);
+        if (e2 == B200MS_OK) {
+          base += 2 * per;
+          continue;
+        }
+        if (e2 != B200MS_EUNSUPPORTED_PAIR) return e2;
+        h->pair_cta = 0;  // e.g. a partition without whole TPCs: the one-CTA kernels below do the same work
       }
-      if (e2 != B200MS_EUNSUPPORTED_PAIR) return e2;
-      h->pair_cta = 0;  // e.g. a partition without whole TPCs: the one-CTA kernels below do the same work
     }
     if (!AT && h->epi_w4 && nm >= 4) {  // four-epilogue-warpgroup form
       if (nm == 4) {

@@ -158,9 +158,9 @@ def test_cta_pair_form_agrees(dtype, unit_rows_, n_pages):
     rng = np.random.default_rng(909 + n_pages)
     lens = ([1, 33, 0, 64, 700, 1030, 2] + list(rng.integers(1, 300, size=50)))[:n_pages]
     pages = make_pages(rng, lens)
-    for n_q in (9, 13, 32, 40, 70):  # 3, 4, 8, 10, 18 query tiles
+    for n_q in (5, 9, 13, 32, 40, 70):  # 2 (pair_cta = 2 only), 3, 4, 8, 10, 18 query tiles
         queries = [unit_rows(rng, 32 if i % 2 else 29) for i in range(n_q)]
-        a = MaxSimIndex(dtype=dtype); a.set_option("pair_cta", 1); a.set_option("unit_rows", unit_rows_); a.add_pages(pages)
+        a = MaxSimIndex(dtype=dtype); a.set_option("pair_cta", 2); a.set_option("unit_rows", unit_rows_); a.add_pages(pages)
         b = MaxSimIndex(dtype=dtype); b.set_option("pair_cta", 0); b.set_option("unit_rows", unit_rows_); b.add_pages(pages)
         ga, gb = a.score_matrix(queries), b.score_matrix(queries)
         assert np.array_equal(ga, gb), (dtype, n_q, np.abs(ga - gb).max())

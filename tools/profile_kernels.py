@@ -22,6 +22,7 @@ ap.add_argument("--pages", type=int, default=32768)
 ap.add_argument("--int8", action="store_true")
 ap.add_argument("--binary", action="store_true")
 ap.add_argument("--reps", type=int, default=4)
+ap.add_argument("--bqs", type=str, default="32,1", help="query batch sizes to drive (bf16 / int8)")
 args = ap.parse_args()
 
 dev = torch.device("cuda", 0)
@@ -43,7 +44,7 @@ def drive(idx, bqs):
 
 idx = MaxSimIndex(dtype="bf16")
 idx.adopt_packed(packed, lens)
-drive(idx, [32, 1])
+drive(idx, [int(b) for b in args.bqs.split(",")])
 rows = packed.view(torch.bfloat16).view(-1, 128)
 if args.int8:
     i8 = MaxSimIndex(dtype="int8")
@@ -54,7 +55,7 @@ if args.int8:
     for r0 in range(0, rows.shape[0], step):
         p8.view(torch.int8).view(-1, 128)[r0:r0 + step] = torch.clamp(torch.round(rows[r0:r0 + step].float() * 127.0), -127, 127).to(torch.int8)
     i8.adopt_packed(p8, lens)
-    drive(i8, [32, 1])
+    drive(i8, [int(b) for b in args.bqs.split(",")])
 if args.binary:
     b1 = MaxSimIndex(dtype="binary")
     bits = torch.empty((rows.shape[0], 16), dtype=torch.uint8, device=dev)
