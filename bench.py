@@ -149,6 +149,15 @@ def build_shard(n_pages: int, device, seed: int, q_host, planted_per_query: int 
 
 
 # ------------------------------------------------------------------------------------------------ reference arm / CPU baseline
+def set_cpu_threads():
+    """torchrun exports OMP_NUM_THREADS=1; the CPU legs are meant to use the host's cores (physical cores by default)."""
+    import torch
+
+    want = int(os.environ.get("B200MS_CPU_THREADS", "0")) or max(1, (os.cpu_count() or 2) // 2)
+    if torch.get_num_threads() != want:
+        torch.set_num_threads(want)
+
+
 def cpu_reference_rate(n_q: int, budget_s: float, seed: int = 1234):
     """patch-vectors/s of the reference's float scorer (score_multi_vector: pad + einsum + max + sum, batch 128) on the host
     CPU with all torch threads, on a bounded sample of the same workload (same generator family / shapes)."""
@@ -156,10 +165,7 @@ def cpu_reference_rate(n_q: int, budget_s: float, seed: int = 1234):
 
     from oracle import maxsim_oracle as orc
 
-    # torchrun exports OMP_NUM_THREADS=1; the reference arm is meant to use the host's cores (physical cores by default)
-    want = int(os.environ.get("B200MS_CPU_THREADS", "0")) or max(1, (os.cpu_count() or 2) // 2)
-    if torch.get_num_threads() != want:
-        torch.set_num_threads(want)
+    set_cpu_threads()
     q = make_queries(n_q).view(n_q, T_TOK, DIM).numpy()
     g = torch.Generator().manual_seed(seed)
 
@@ -182,6 +188,46 @@ def cpu_reference_rate(n_q: int, budget_s: float, seed: int = 1234):
     dt = time.perf_counter() - t0
     return {"value": n_pages * P_PATCH / dt, "seconds": dt, "pages": n_pages, "threads": torch.get_num_threads(),
             "checksum": float(scores.sum())}
+
+
+def config0_latency(packed, q_pin, out_pin, k, skip_cpu, n_pages=100, iters=300):
+    """BASELINE configs[0] (N=100 pages x 1024 x 128, B_q=1, T=32): per-call latency of b200ms_search_host on the first
+    100 pages of the shard (host query in, host top-k out), and the reference's CPU formulation on the same shapes."""
+    import numpy as np
+    import torch
+
+    from morphik_core_b200.index import MaxSimIndex
+
+    idx0 = MaxSimIndex(device=packed.device.index or 0, dtype="bf16")
+    idx0.adopt_packed(packed[: n_pages * P_PATCH * DIM * 2], [P_PATCH] * n_pages)
+    q1 = q_pin[:T_TOK]
+    o = (out_pin[0][:1], out_pin[1][:1], out_pin[2][:1])
+    for _ in range(20):
+        idx0.search_host_flat(q1, [T_TOK], k, *o)
+    lat = []
+    for _ in range(iters):
+        t0 = time.perf_counter()
+        idx0.search_host_flat(q1, [T_TOK], k, *o)
+        lat.append(time.perf_counter() - t0)
+    lat = np.sort(np.asarray(lat)) * 1e6
+    kern = idx0.score_times_ms(64)
+    out = {"workload": f"configs[0]: {n_pages} pages x {P_PATCH} patches x {DIM}-d bf16, 1 query x {T_TOK} tokens, top-{k}",
+           "api": "b200ms_search_host (host query in, host top-k out)", "e2e_p50_us": float(lat[len(lat) // 2]),
+           "e2e_p95_us": float(lat[int(len(lat) * 0.95)]), "scoring_kernel_us": 1e3 * sum(kern) / len(kern), "calls": iters}
+    if not skip_cpu:
+        from oracle import maxsim_oracle as orc
+
+        set_cpu_threads()
+        qn = q1.view(1, T_TOK, DIM).numpy()
+        pages = packed[: n_pages * P_PATCH * DIM * 2].view(torch.bfloat16).view(n_pages, P_PATCH, DIM).float().cpu().numpy()
+        ts = []
+        for _ in range(5):
+            t0 = time.perf_counter()
+            orc.score_multi_vector_port_dense(qn, pages)
+            ts.append(time.perf_counter() - t0)
+        out["cpu_reference_formulation_ms"] = 1e3 * sorted(ts)[len(ts) // 2]
+        out["cpu_threads"] = torch.get_num_threads()
+    return out
 
 
 def torch_gpu_reference_rate(rows_bf16, q_dev, n_q, sample_pages=4096, iters=5):
@@ -425,6 +471,15 @@ def run_gpu(args):
                "traffic": (tr["maxsim_umma<bf16,NM=1>"]["dram_bytes_per_patch_vector"] * rows
                            if tr and "maxsim_umma<bf16,NM=1>" in tr else None)}
 
+    # ---- configs[0], the reference's own CPU-runnable case (100 pages, one 32-token query): single-call latency through the
+    #      C-ABI with host buffers, next to the reference formulation on the host CPU for the same shapes
+    cfg0 = None
+    if rank == 0 and world == 1:
+        try:
+            cfg0 = config0_latency(packed, q_pin, out_pin, k, args.no_cpu_baseline)
+        except Exception as e:  # noqa: BLE001  (an extra leg must never break the bench line)
+            cfg0 = {"error": repr(e)[:200]}
+
     # ---- the reference's own GPU formulation on the same GPU (rank 0, N=1 only)
     torch_gpu = None
     if rank == 0 and world == 1:
@@ -450,7 +505,7 @@ def run_gpu(args):
                     "api": "b200ms_search_host (C-ABI, pinned host buffers)" if world == 1 else
                            "pinned H2D + ShardedMaxSim.search (NCCL all-gather + merge) + D2H"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "hbm_regime": hbm, "cpu_baseline": cpu,
-            "torch_gpu_reference_formulation": torch_gpu,
+            "torch_gpu_reference_formulation": torch_gpu, "config0_latency": cfg0,
             "page_scores_per_sec": value / P_PATCH * n_q, "top1_sample": top1[:4],
         }
         print(json.dumps(line), flush=True)

@@ -345,12 +345,17 @@ B200MS_API int b200ms_set_corpus(b200ms_t* h, const void* rows, int dtype, const
   c.n_chunks = c.n_rows / kGroup;
   if (c.n_chunks >= (int64_t(1) << 31)) return set_error(h, B200MS_EINVAL, "set_corpus: more than 2^31 chunks");
   // work units: runs of whole pages of about unit_rows rows; unit_start in chunks
+  // (small corpora: shrink the units so that every SM still gets about four of them -- a 100-page corpus as 25 units
+  // of 4096 rows would leave 123 SMs idle)
+  int64_t unit_rows = c.n_rows / (4 * int64_t(h->num_sms > 0 ? h->num_sms : 1));
+  if (unit_rows < kTileN) unit_rows = kTileN;
+  if (unit_rows > h->unit_rows) unit_rows = h->unit_rows;
   std::vector<int32_t> us;
   us.push_back(0);
   int64_t acc = 0;
   for (int64_t i = 0; i < n_pages; ++i) {
     acc += ps[i + 1] - ps[i];
-    if (acc >= h->unit_rows) {
+    if (acc >= unit_rows) {
       us.push_back(int32_t(ps[i + 1] / kGroup));
       acc = 0;
     }
