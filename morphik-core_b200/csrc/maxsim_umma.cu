@@ -39,27 +39,6 @@ constexpr int kThreads = 384;
 //             32-row quarters of the tile, so every lane quadrant of the accumulator holds the same tokens and each of the
 //             four epilogue warps reduces one 32-column chunk in parallel (instead of warp 0 walking all four); the chunk
 //             maxima meet in a shared-memory slab once per tile and warp 0 applies the page logic.
-// max over 32 of the 64 columns held in v (offset O), four independent chains
-template <typename Acc, int O>
-__device__ __forceinline__ Acc chunk_max64(const uint32_t (&v)[64]) {
-  Acc a = acc_from_bits(v[O], Acc{}), b = acc_from_bits(v[O + 1], Acc{});
-  Acc c = acc_from_bits(v[O + 2], Acc{}), d = acc_from_bits(v[O + 3], Acc{});
-#pragma unroll
-  for (int i = 4; i < 28; i += 8) {
-    a = acc_max3(a, acc_from_bits(v[O + i], Acc{}), acc_from_bits(v[O + i + 1], Acc{}));
-    b = acc_max3(b, acc_from_bits(v[O + i + 2], Acc{}), acc_from_bits(v[O + i + 3], Acc{}));
-    c = acc_max3(c, acc_from_bits(v[O + i + 4], Acc{}), acc_from_bits(v[O + i + 5], Acc{}));
-    d = acc_max3(d, acc_from_bits(v[O + i + 6], Acc{}), acc_from_bits(v[O + i + 7], Acc{}));
-  }
-  a = acc_max3(a, acc_from_bits(v[O + 28], Acc{}), acc_from_bits(v[O + 29], Acc{}));
-  b = acc_max3(b, acc_from_bits(v[O + 30], Acc{}), acc_from_bits(v[O + 31], Acc{}));
-  return acc_max(acc_max(a, b), acc_max(c, d));
-}
-
-#ifndef B200MS_EPI_V2
-#define B200MS_EPI_V2 0  // measured slower (profiles/r01/README.md): x64 loads + setmaxnreg 72/208 spill in the control warps
-#endif
-
 template <int KIND, int NM, bool AT, bool S4>
 __global__ void __launch_bounds__(kThreads, 1)
 maxsim_umma_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constant__ CUtensorMap tmap_q,
@@ -113,11 +92,6 @@ maxsim_umma_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_c
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-#if B200MS_EPI_V2
-  // warps 0-3 (TMA, MMA, TMEM alloc, idle) need few registers; the two epilogue warpgroups hold a whole 128-column
-  // accumulator row (128 registers) per thread: 128*72 + 256*208 = 62464 <= 65536
-  if (warp < 4) setmaxnreg_dec<72>(); else setmaxnreg_inc<208>();
-#endif
   if (warp == 0) {
     // ================================================================ TMA producer
     if (lane == 0) {
@@ -347,31 +321,6 @@ maxsim_umma_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_c
               tc_fence_after();
               if (active) {
                 const uint32_t taddr = lane_base + kAccCol0 + buf * kAccN;
-#if B200MS_EPI_V2
-                if constexpr (kHalves == 1) {
-                  // whole accumulator row in registers: both loads in flight, ONE wait, buffer released before any math
-                  uint32_t v0[64], v1[64];
-                  tmem_ld_32x64(taddr, v0);
-                  tmem_ld_32x64(taddr + 64, v1);
-                  tmem_ld_wait();
-                  tc_fence_before();
-                  __syncwarp();
-                  if (lane == 0) mbar_arrive(&tempty[buf]);
-                  cm[0] = chunk_max64<Acc, 0>(v0);
-                  cm[1] = chunk_max64<Acc, 32>(v0);
-                  cm[2] = chunk_max64<Acc, 0>(v1);
-                  cm[3] = chunk_max64<Acc, 32>(v1);
-                } else {
-                  uint32_t v0[64];
-                  tmem_ld_32x64(taddr, v0);
-                  tmem_ld_wait();
-                  tc_fence_before();
-                  __syncwarp();
-                  if (lane == 0) mbar_arrive(&tempty[buf]);
-                  cm[2 * hf] = chunk_max64<Acc, 0>(v0);
-                  cm[2 * hf + 1] = chunk_max64<Acc, 32>(v0);
-                }
-#else
                 uint32_t va[32], vb[32];
                 tmem_ld_32x32(taddr, va);
                 tmem_ld_32x32(taddr + 32, vb);
@@ -388,7 +337,6 @@ maxsim_umma_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_c
                 if (lane == 0) mbar_arrive(&tempty[buf]);  // accumulator drained: MMA may overwrite it
                 cm[kHalves == 1 ? 2 : 2 * hf] = chunk_max<Acc>(va);
                 cm[kHalves == 1 ? 3 : 2 * hf + 1] = chunk_max<Acc>(vb);
-#endif
               } else {
                 tc_fence_before();
                 __syncwarp();
