@@ -139,6 +139,16 @@ int b200ms_search_host(b200ms_t* h, const float* q_host, const int32_t* q_lens, 
                        const uint32_t* allow_mask_host, float i8_q_scale, float score_scale, int64_t id_base,
                        float* top_scores_host, int64_t* top_ids_host, int32_t* top_counts_host);
 
+/* b200ms_search_host with ONE allow-mask PER QUERY: allow_masks_host is a [n_masks, ceil(n_pages/32)] matrix of page
+ * bitmasks, mask_index_host[i] the row that filters query i (-1 = unfiltered); n_masks = 0 means no filtering at all.
+ * The production caller always passes the requesting user's authorised doc_ids (core/services/document_service.py:408-417),
+ * so concurrent query_similar calls carry DIFFERENT filters; with per-query masks they still share one pass over the
+ * corpus (four 32-token queries fit one 128-row MMA tile and cost the same as one). */
+int b200ms_search_host_masked(b200ms_t* h, const float* q_host, const int32_t* q_lens, int n_q, int k,
+                              const uint32_t* allow_masks_host, int n_masks, const int32_t* mask_index_host,
+                              float i8_q_scale, float score_scale, int64_t id_base, float* top_scores_host,
+                              int64_t* top_ids_host, int32_t* top_counts_host);
+
 /* Same with everything on the device and no synchronisation (enqueued on `stream`).  q_dev: F32|BF16. */
 int b200ms_search_device(b200ms_t* h, const void* q_dev, int src_dtype, const int32_t* q_lens, int n_q, int k,
                          const uint32_t* allow_mask_dev, float i8_q_scale, float score_scale, int64_t id_base,

@@ -10,6 +10,7 @@ core/vector_store/multi_vector_store.py:240-251) lives here, together with:
 """
 from __future__ import annotations
 
+from collections import OrderedDict
 from dataclasses import dataclass, field
 from typing import Any, Dict, Iterable, List, Optional, Sequence, Tuple
 
@@ -33,6 +34,13 @@ class PageCatalog:
         self._n = 0
         self._by_doc: Dict[str, List[int]] = {}
         self._by_key: Dict[Tuple[str, int], int] = {}
+        # columnar copies of document_id / app_id as small integers: the doc_ids filter becomes one table gather
+        self._doc_index: Dict[str, int] = {}
+        self._app_index: Dict[str, int] = {}
+        self._page_doc = np.zeros(0, dtype=np.int32)
+        self._page_app = np.zeros(0, dtype=np.int32)  # -1 = stored without an app_id (visible to everybody)
+        self.version = 0  # bumped by every mutation; keys the mask cache
+        self._mask_cache: "OrderedDict[Tuple, Optional[np.ndarray]]" = OrderedDict()
 
     # ------------------------------------------------------------------ size
     def __len__(self) -> int:
@@ -50,18 +58,24 @@ class PageCatalog:
     def add(self, rec: PageRecord) -> int:
         pid = self._n
         if pid >= self.alive.shape[0]:
-            grown = np.zeros(max(1024, 2 * self.alive.shape[0]), dtype=bool)
-            grown[: self._n] = self.alive[: self._n]
-            self.alive = grown
+            cap = max(1024, 2 * self.alive.shape[0])
+            for name, dt in (("alive", bool), ("_page_doc", np.int32), ("_page_app", np.int32)):
+                grown = np.zeros(cap, dtype=dt)
+                grown[: self._n] = getattr(self, name)[: self._n]
+                setattr(self, name, grown)
         self.records.append(rec)
         self.alive[pid] = True
+        self._page_doc[pid] = self._doc_index.setdefault(rec.document_id, len(self._doc_index))
+        self._page_app[pid] = -1 if rec.app_id is None else self._app_index.setdefault(rec.app_id, len(self._app_index))
         self._n += 1
+        self.version += 1
         self._by_doc.setdefault(rec.document_id, []).append(pid)
         self._by_key[(rec.document_id, int(rec.chunk_number))] = pid  # a re-insert of the same key shadows the old page
         return pid
 
     def delete_document(self, document_id: str) -> List[int]:
         pids = self._by_doc.pop(document_id, [])
+        self.version += 1
         for pid in pids:
             self.alive[pid] = False
             rec = self.records[pid]
@@ -87,16 +101,32 @@ class PageCatalog:
         n = self._n
         mask = self.alive[:n].copy()
         if doc_ids is not None:
-            sel = np.zeros(n, dtype=bool)
-            for d in dict.fromkeys(doc_ids):
-                ids = self._by_doc.get(d)
-                if ids:
-                    sel[ids] = True
-            mask &= sel
+            lut = np.zeros(len(self._doc_index) + 1, dtype=bool)
+            idx = [self._doc_index[d] for d in doc_ids if d in self._doc_index]
+            if idx:
+                lut[idx] = True
+            mask &= lut[self._page_doc[:n]]
         if app_id is not None:
-            foreign = np.fromiter((r.app_id is not None and r.app_id != app_id for r in self.records), dtype=bool, count=n)
-            mask &= ~foreign
+            mine = self._app_index.get(app_id, -2)
+            pa = self._page_app[:n]
+            mask &= (pa < 0) | (pa == mine)
         return None if mask.all() else mask
+
+    def allow_words(self, doc_ids: Optional[Sequence[str]] = None, app_id: Optional[str] = None
+                    ) -> Tuple[bool, Optional[np.ndarray]]:
+        """(any page visible?, device filter words or None = unfiltered) with a small LRU: a user's authorised document
+        list (document_service.py:408-417) repeats from query to query, so the mask is usually a dictionary hit."""
+        key = (self.version, app_id, None if doc_ids is None else tuple(doc_ids))
+        hit = self._mask_cache.get(key, False)
+        if hit is not False:
+            self._mask_cache.move_to_end(key)
+            return hit
+        mask = self.allow_mask(doc_ids, app_id)
+        val = (True, None) if mask is None else (bool(mask.any()), self.mask_words(mask))
+        self._mask_cache[key] = val
+        while len(self._mask_cache) > 64:
+            self._mask_cache.popitem(last=False)
+        return val
 
     @staticmethod
     def mask_words(mask: np.ndarray) -> np.ndarray:
@@ -118,7 +148,11 @@ class PageCatalog:
     def apply_compaction(self, keep: Iterable[int]) -> None:
         old = self.records
         self.records, self._by_doc, self._by_key = [], {}, {}
+        self._doc_index, self._app_index = {}, {}
         self.alive = np.zeros(0, dtype=bool)
+        self._page_doc = np.zeros(0, dtype=np.int32)
+        self._page_app = np.zeros(0, dtype=np.int32)
+        self._mask_cache.clear()
         self._n = 0
         for pid in keep:
             self.add(old[int(pid)])

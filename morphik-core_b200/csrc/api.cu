@@ -507,7 +507,8 @@ B200MS_API int b200ms_merge_topk(b200ms_t* h, const float* cand_scores, const in
 
 static int search_impl(b200ms_t* h, const void* q_dev, int src_dtype, const int32_t* q_lens, int n_q, int k,
                        const uint32_t* allow_dev, float i8_q_scale, float score_scale, int64_t id_base, float* ts,
-                       int64_t* ti, int32_t* tc, cudaStream_t s, const int64_t* cand_ids = nullptr, int n_cand = 0) {
+                       int64_t* ti, int32_t* tc, cudaStream_t s, const int64_t* cand_ids = nullptr, int n_cand = 0,
+                       const int32_t* mask_index_dev = nullptr, int64_t mask_stride = 0) {
   const Corpus& c = h->corpus;
   if (c.dtype < 0) return set_error(h, B200MS_ESTATE, "search: no corpus attached (call b200ms_set_corpus first)");
   if (n_q < 1 || !q_lens || !q_dev || k < 1 || k > B200MS_MAX_K || !ts || !ti || !tc)
@@ -527,7 +528,11 @@ static int search_impl(b200ms_t* h, const void* q_dev, int src_dtype, const int3
     if (int e = check_cuda(h, cudaMemsetAsync(h->scores.p, 0, size_t(groups_padded > 0 ? groups_padded : 4) * size_t(ld > 0 ? ld : 32) * 4, s), "search: memset")) return e;
   }
   const int sdt = c.dtype == B200MS_BF16 ? B200MS_F32 : B200MS_I32;
-  if (!cand_ids) return b200ms_topk(h, h->scores.p, sdt, c.n_pages, ld, goff.data(), n_q, allow_dev, k, score_scale, id_base, ts, ti, tc, s);
+  if (!cand_ids) {
+    if (int e = upload(h, h->meta_a, goff.data(), size_t(n_q + 1) * 4, s)) return e;
+    return launch_topk(h, h->scores.p, sdt, c.n_pages, ld, static_cast<const int32_t*>(h->meta_a.p), n_q, allow_dev, k,
+                       score_scale, id_base, nullptr, ts, ti, tc, s, mask_index_dev, mask_stride);
+  }
   // candidate mode: rank the slots (ties -> lower slot = better first-stage rank), report the page ids; unused slots masked
   if (int e = reserve(h, h->cand_mask, size_t((n_cand + 31) / 32) * 4)) return e;
   if (int e = launch_cand_units(h, cand_ids, n_cand, nullptr, nullptr, static_cast<uint32_t*>(h->cand_mask.p), s)) return e;
@@ -557,10 +562,10 @@ B200MS_API int b200ms_search_device(b200ms_t* h, const void* q_dev, int src_dtyp
                      top_ids_dev, top_counts_dev, static_cast<cudaStream_t>(stream));
 }
 
-B200MS_API int b200ms_search_host(b200ms_t* h, const float* q_host, const int32_t* q_lens, int n_q, int k,
-                                  const uint32_t* allow_mask_host, float i8_q_scale, float score_scale, int64_t id_base,
-                                  float* top_scores_host, int64_t* top_ids_host, int32_t* top_counts_host) {
-  if (!h) return B200MS_EINVAL;
+static int search_host_impl(b200ms_t* h, const float* q_host, const int32_t* q_lens, int n_q, int k,
+                            const uint32_t* masks_host, int n_masks, const int32_t* mask_index_host, float i8_q_scale,
+                            float score_scale, int64_t id_base, float* top_scores_host, int64_t* top_ids_host,
+                            int32_t* top_counts_host) {
   if (n_q < 1 || !q_lens || !q_host || k < 1 || k > B200MS_MAX_K || !top_scores_host || !top_ids_host || !top_counts_host)
     return set_error(h, B200MS_EINVAL, "search_host: bad arguments (n_q >= 1, 1 <= k <= 4096)");
   DeviceGuard g(h->device);
@@ -574,18 +579,46 @@ B200MS_API int b200ms_search_host(b200ms_t* h, const float* q_host, const int32_
   if (rows > 0)
     if (int e = check_cuda(h, cudaMemcpyAsync(h->q_raw.p, q_host, size_t(rows) * kDim * 4, cudaMemcpyHostToDevice, s), "search_host: H2D queries")) return e;
   const uint32_t* allow_dev = nullptr;
-  if (allow_mask_host && h->corpus.n_pages > 0) {
-    if (int e = upload(h, h->mask, allow_mask_host, size_t((h->corpus.n_pages + 31) / 32) * 4, s)) return e;
+  const int32_t* index_dev = nullptr;
+  const int64_t words = (h->corpus.n_pages + 31) / 32;
+  if (masks_host && n_masks > 0 && h->corpus.n_pages > 0) {
+    if (int e = upload(h, h->mask, masks_host, size_t(n_masks) * size_t(words) * 4, s)) return e;
     allow_dev = static_cast<const uint32_t*>(h->mask.p);
+    if (mask_index_host) {
+      for (int i = 0; i < n_q; ++i)
+        if (mask_index_host[i] < -1 || mask_index_host[i] >= n_masks)
+          return set_error(h, B200MS_EINVAL, "search_host_masked: mask_index out of range");
+      if (int e = upload(h, h->mask_index, mask_index_host, size_t(n_q) * 4, s)) return e;
+      index_dev = static_cast<const int32_t*>(h->mask_index.p);
+    }
   }
   if (int e = search_impl(h, h->q_raw.p, B200MS_F32, q_lens, n_q, k, allow_dev, i8_q_scale, score_scale, id_base,
                           static_cast<float*>(h->out_s.p), static_cast<int64_t*>(h->out_i.p),
-                          static_cast<int32_t*>(h->out_c.p), s))
+                          static_cast<int32_t*>(h->out_c.p), s, nullptr, 0, index_dev, words))
     return e;
   cudaMemcpyAsync(top_scores_host, h->out_s.p, size_t(n_q) * k * 4, cudaMemcpyDeviceToHost, s);
   cudaMemcpyAsync(top_ids_host, h->out_i.p, size_t(n_q) * k * 8, cudaMemcpyDeviceToHost, s);
   cudaMemcpyAsync(top_counts_host, h->out_c.p, size_t(n_q) * 4, cudaMemcpyDeviceToHost, s);
   return check_cuda(h, cudaStreamSynchronize(s), "search_host: stream sync");
+}
+
+B200MS_API int b200ms_search_host(b200ms_t* h, const float* q_host, const int32_t* q_lens, int n_q, int k,
+                                  const uint32_t* allow_mask_host, float i8_q_scale, float score_scale, int64_t id_base,
+                                  float* top_scores_host, int64_t* top_ids_host, int32_t* top_counts_host) {
+  if (!h) return B200MS_EINVAL;
+  return search_host_impl(h, q_host, q_lens, n_q, k, allow_mask_host, allow_mask_host ? 1 : 0, nullptr, i8_q_scale,
+                          score_scale, id_base, top_scores_host, top_ids_host, top_counts_host);
+}
+
+B200MS_API int b200ms_search_host_masked(b200ms_t* h, const float* q_host, const int32_t* q_lens, int n_q, int k,
+                                         const uint32_t* allow_masks_host, int n_masks, const int32_t* mask_index_host,
+                                         float i8_q_scale, float score_scale, int64_t id_base, float* top_scores_host,
+                                         int64_t* top_ids_host, int32_t* top_counts_host) {
+  if (!h) return B200MS_EINVAL;
+  if (n_masks < 0 || (n_masks > 0 && (!allow_masks_host || !mask_index_host)))
+    return set_error(h, B200MS_EINVAL, "search_host_masked: n_masks > 0 needs the mask matrix and one index per query");
+  return search_host_impl(h, q_host, q_lens, n_q, k, allow_masks_host, n_masks, mask_index_host, i8_q_scale, score_scale,
+                          id_base, top_scores_host, top_ids_host, top_counts_host);
 }
 
 // ------------------------------------------------------------------------------------------------ FDE (next row f-1)

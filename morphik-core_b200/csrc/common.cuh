@@ -55,7 +55,7 @@ struct b200ms {
   bms::DeviceBuf page_start;   // int64 [n_pages+1]  first padded row of every page   (B1 kernel, pack)
   // scratch for pack / search
   bms::DeviceBuf meta_a, meta_b, meta_c;  // small int arrays uploaded per call
-  bms::DeviceBuf q_raw, q_packed, scores, mask, out_s, out_i, out_c;
+  bms::DeviceBuf q_raw, q_packed, scores, mask, mask_index, out_s, out_i, out_c;
   bms::DeviceBuf topk_keys, topk_ids;  // first-level (per-slice) top-k candidates
   bms::DeviceBuf b1_q_i8, b1_tok_const;  // tensor-core 1-bit scorer: +-1 int8 query tiles and per-token constants
   bms::DeviceBuf cand_start, cand_end, cand_mask;  // candidate (rerank) mode: per-slot chunk ranges, valid-slot bitmask
@@ -108,7 +108,7 @@ int launch_pack_rows(b200ms_t* h, const void* src, int src_dtype, const int64_t*
 int launch_topk(b200ms_t* h, const void* group_scores, int score_dtype, int64_t n_pages, int64_t ld,
                 const int32_t* group_offsets_dev, int n_q, const uint32_t* allow_mask, int k, float scale,
                 int64_t id_base, const int64_t* id_map, float* top_scores, int64_t* top_ids, int32_t* top_counts,
-                cudaStream_t s);
+                cudaStream_t s, const int32_t* mask_index = nullptr, int64_t mask_stride = 0);
 int launch_fde_encode(b200ms_t* h, const void* rows, int src_dtype, const int64_t* item_start_dev, int n_items,
                       int is_document, float* out, cudaStream_t s);
 int launch_fde_finalize(b200ms_t* h, const float* fde, int64_t n, void* out_rows, float* inv_norm, cudaStream_t s);

@@ -63,9 +63,10 @@ __device__ void bitonic_desc_u64(uint64_t* a, int n2) {
 template <typename T>
 __global__ void __launch_bounds__(kTopkThreads)
 topk_kernel(const T* __restrict__ gs, int64_t n_pages, int64_t ld, const int32_t* __restrict__ group_offsets,
-            const uint32_t* __restrict__ allow, int k, float scale, int64_t id_base, const int64_t* __restrict__ id_map,
+            const uint32_t* __restrict__ allow_base, int k, float scale, int64_t id_base, const int64_t* __restrict__ id_map,
             float* __restrict__ top_scores, int64_t* __restrict__ top_ids, int32_t* __restrict__ top_counts,
-            int64_t slice_pages, uint32_t* __restrict__ part_keys, int64_t* __restrict__ part_ids) {
+            int64_t slice_pages, uint32_t* __restrict__ part_keys, int64_t* __restrict__ part_ids,
+            const int32_t* __restrict__ mask_index, int64_t mask_stride) {
   // grid = (n_q, n_slices): CTA (q, s) selects the exact top-k of pages [s*slice_pages, (s+1)*slice_pages).  With one slice
   // it writes the final result; otherwise (raw key, id) candidates for topk_merge_kernel (global top-k is a subset of the
   // union of the slices' top-k, and both levels order by (key DESC, id ASC), so the result is identical).
@@ -75,6 +76,12 @@ topk_kernel(const T* __restrict__ gs, int64_t n_pages, int64_t ld, const int32_t
   __shared__ uint32_t warp_cnt[kTopkThreads / 32];
 
   const int q = blockIdx.x;
+  // one allow-mask for every query (mask_index == NULL), or a row of a mask matrix per query (-1 = unfiltered)
+  const uint32_t* allow = allow_base;
+  if (mask_index && allow_base) {
+    const int mi = __ldg(mask_index + q);
+    allow = mi >= 0 ? allow_base + int64_t(mi) * mask_stride : nullptr;
+  }
   const int g0 = group_offsets[q], g1 = group_offsets[q + 1];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int64_t pbeg = int64_t(blockIdx.y) * slice_pages;
@@ -279,7 +286,7 @@ static int launch_merge_impl(b200ms_t* h, const float* cand_scores, const uint32
 int launch_topk(b200ms_t* h, const void* group_scores, int score_dtype, int64_t n_pages, int64_t ld,
                 const int32_t* group_offsets_dev, int n_q, const uint32_t* allow_mask, int k, float scale,
                 int64_t id_base, const int64_t* id_map, float* top_scores, int64_t* top_ids, int32_t* top_counts,
-                cudaStream_t s) {
+                cudaStream_t s, const int32_t* mask_index, int64_t mask_stride) {
   if (n_q <= 0) return B200MS_OK;
   int n2 = 1;
   while (n2 < k) n2 <<= 1;
@@ -304,11 +311,12 @@ int launch_topk(b200ms_t* h, const void* group_scores, int score_dtype, int64_t 
   if (score_dtype == B200MS_F32) {
     topk_kernel<float><<<grid, kTopkThreads, smem, s>>>(static_cast<const float*>(group_scores), n_pages, ld,
                                                        group_offsets_dev, allow_mask, k, scale, id_base, id_map, top_scores,
-                                                       top_ids, top_counts, slice_pages, part_keys, part_ids);
+                                                       top_ids, top_counts, slice_pages, part_keys, part_ids, mask_index,
+                                                       mask_stride);
   } else {
     topk_kernel<int><<<grid, kTopkThreads, smem, s>>>(static_cast<const int*>(group_scores), n_pages, ld, group_offsets_dev,
                                                      allow_mask, k, scale, id_base, id_map, top_scores, top_ids, top_counts,
-                                                     slice_pages, part_keys, part_ids);
+                                                     slice_pages, part_keys, part_ids, mask_index, mask_stride);
   }
   h->launches++;
   if (int e = check_cuda(h, cudaGetLastError(), "launch topk")) return e;

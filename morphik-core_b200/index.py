@@ -268,6 +268,43 @@ class MaxSimIndex:
         )
         return ts, ti, tc
 
+    def search_host_masked(self, queries: Sequence[np.ndarray], k: int, allow_masks: Sequence[Optional[np.ndarray]],
+                           id_base: int = 0):
+        """search_host with one allow-mask PER QUERY (``allow_masks[i]``: uint32 words as for ``allow_mask``, or None =
+        unfiltered): queries of different users -- different authorised ``doc_ids`` (document_service.py:408-417) -- share one
+        pass over the corpus.  Identical mask objects/contents are uploaded once."""
+        self._attach()
+        lens = self._q_lens(queries)
+        n_q = len(lens)
+        if len(allow_masks) != n_q:
+            raise ValueError("one allow-mask (or None) per query")
+        q_host = np.ascontiguousarray(np.concatenate([np.asarray(q, dtype=np.float32) for q in queries], axis=0))
+        words = (self.n_pages + 31) // 32
+        rows, index, seen = [], [], {}
+        for m in allow_masks:
+            if m is None:
+                index.append(-1)
+                continue
+            m = np.ascontiguousarray(m, dtype=np.uint32)
+            if m.shape != (words,):
+                raise ValueError(f"allow-mask must have {words} uint32 words, got {m.shape}")
+            key = m.tobytes()
+            if key not in seen:
+                seen[key] = len(rows)
+                rows.append(m)
+            index.append(seen[key])
+        ts, ti, tc = np.empty((n_q, k), np.float32), np.empty((n_q, k), np.int64), np.empty((n_q,), np.int32)
+        mat = np.stack(rows) if rows else None
+        self.h.check(
+            nat.lib.b200ms_search_host_masked(
+                self.h.ptr, q_host.ctypes.data_as(ctypes.c_void_p), nat.i32_array(lens), n_q, int(k),
+                None if mat is None else mat.ctypes.data_as(ctypes.c_void_p), len(rows), nat.i32_array(index),
+                ctypes.c_float(self.i8_scale), ctypes.c_float(self.score_scale), int(id_base),
+                ts.ctypes.data_as(ctypes.c_void_p), ti.ctypes.data_as(ctypes.c_void_p), tc.ctypes.data_as(ctypes.c_void_p)),
+            "b200ms_search_host_masked",
+        )
+        return ts, ti, tc
+
     def search_host_flat(self, q_host: Union[np.ndarray, torch.Tensor], q_lens: Sequence[int], k: int,
                          out_scores: torch.Tensor, out_ids: torch.Tensor, out_counts: torch.Tensor,
                          allow_mask: Optional[np.ndarray] = None, id_base: int = 0):

@@ -14,14 +14,21 @@ argument names/meaning, same return shapes) plus the de-facto extras callers use
 Everything heavy runs on the GPU through libb200ms (see index.py); this class only owns the id <-> (document, chunk)
 catalogue, the doc_ids -> page-mask conversion, payload bookkeeping and DocumentChunk construction.  GPU calls are
 serialised with a lock and pushed off the event loop with asyncio.to_thread (SURVEY 8b "Threading").
+
+Concurrent ``query_similar`` coroutines (the API server's situation) are COALESCED: while one GPU pass is running, the
+requests that arrive queue up and the next pass scores them together, each against its own authorised-page mask
+(``b200ms_search_host_masked``).  A single 32-token query leaves 3/4 of every 128-row MMA tile empty and the scan is
+HBM-bound, so up to ~8 queries ride for the price of one; a lone query is not delayed (there is no batching window).
 """
 from __future__ import annotations
 
 import asyncio
+import collections
 import json
 import logging
 import threading
 import time
+import weakref
 from typing import Any, Dict, List, Optional, Sequence, Tuple, Union
 
 import numpy as np
@@ -100,12 +107,29 @@ def as_page_matrix(embedding):
     return emb[None, :] if emb.ndim == 1 else emb
 
 
+class _QueryRequest:
+    __slots__ = ("q", "k", "doc_ids", "app_id", "future")
+
+    def __init__(self, q, k, doc_ids, app_id, future):
+        self.q, self.k, self.doc_ids, self.app_id, self.future = q, k, doc_ids, app_id, future
+
+
+class _LoopQueue:
+    """Pending query_similar requests of ONE event loop and the task that drains them."""
+    __slots__ = ("pending", "task", "__weakref__")
+
+    def __init__(self):
+        self.pending = collections.deque()
+        self.task = None
+
+
 class B200MultiVectorStore(BaseVectorStore):
     """Exhaustive ColPali MaxSim store on one B200 (see module docstring)."""
 
     def __init__(self, uri: str = "b200://0", device: int = 0, mode: str = "bf16", storage: Any = None,
                  auto_initialize: bool = True, compact_dead_fraction: float = 0.3, index: Any = None,
-                 fde_candidates: Optional[int] = None):
+                 fde_candidates: Optional[int] = None, coalesce_queries: bool = True, max_coalesced_tokens: int = 1024,
+                 max_coalesced_queries: int = 64):
         self.uri = uri
         self.device = int(device)
         self.mode = mode
@@ -117,6 +141,13 @@ class B200MultiVectorStore(BaseVectorStore):
         # the "morphik" provider -- FDE candidates (the reference asks Turbopuffer for min(10*k, 75)) then MaxSim rerank.
         self.fde_candidates = fde_candidates
         self._two_stage = None
+        # concurrent query_similar calls share GPU passes (see module docstring); 1024 tokens = one CTA-pair pass
+        self.coalesce_queries = bool(coalesce_queries)
+        self.max_coalesced_tokens = int(max_coalesced_tokens)
+        self.max_coalesced_queries = int(max_coalesced_queries)
+        self._queues: "weakref.WeakKeyDictionary[Any, _LoopQueue]" = weakref.WeakKeyDictionary()
+        self._queues_lock = threading.Lock()
+        self.last_coalesced_batch = 0
         self._lock = threading.Lock()
         self._last_store_metrics: Dict[str, Any] = {}
         self.last_query_timing: Dict[str, float] = {}
@@ -179,8 +210,90 @@ class B200MultiVectorStore(BaseVectorStore):
     # ------------------------------------------------------------------ read path
     async def query_similar(self, query_embedding, k: int, doc_ids: Optional[List[str]] = None,
                             app_id: Optional[str] = None, skip_image_content: bool = False) -> List[DocumentChunk]:
-        results = await self.query_similar_batch([query_embedding], k, doc_ids, app_id, skip_image_content)
-        return results[0]
+        if not self.coalesce_queries:
+            results = await self.query_similar_batch([query_embedding], k, doc_ids, app_id, skip_image_content)
+            return results[0]
+        q = as_query_matrix(query_embedding)
+        if k <= 0:
+            return []
+        loop = asyncio.get_running_loop()
+        with self._queues_lock:
+            lq = self._queues.get(loop)
+            if lq is None:
+                lq = self._queues[loop] = _LoopQueue()
+        req = _QueryRequest(q, int(k), doc_ids, app_id, loop.create_future())
+        lq.pending.append(req)
+        if lq.task is None or lq.task.done():
+            lq.task = loop.create_task(self._drain(lq))
+        return await req.future
+
+    async def _drain(self, lq: _LoopQueue) -> None:
+        """Score everything that is pending, one GPU pass per batch; requests arriving meanwhile form the next batch."""
+        while lq.pending:
+            batch, tokens = [], 0
+            while lq.pending and len(batch) < self.max_coalesced_queries:
+                nxt = lq.pending[0]
+                if batch and tokens + nxt.q.shape[0] > self.max_coalesced_tokens:
+                    break
+                batch.append(lq.pending.popleft())
+                tokens += nxt.q.shape[0]
+            try:
+                results = await asyncio.to_thread(self._search_coalesced_locked, batch)
+            except BaseException as e:  # noqa: BLE001  (every waiter must be released; errors propagate like the reference's)
+                for r in batch:
+                    if not r.future.done():
+                        r.future.set_exception(e if isinstance(e, Exception) else RuntimeError(repr(e)))
+                if not isinstance(e, Exception):
+                    raise
+                continue
+            for r, res in zip(batch, results):
+                if not r.future.done():
+                    r.future.set_result(res)
+
+    def _search_coalesced_locked(self, batch: List[_QueryRequest]) -> List[List[DocumentChunk]]:
+        """One pass for a batch of independent requests; masks are built under the lock so they match the corpus."""
+        t0 = time.perf_counter()
+        with self._lock:
+            n = len(self.catalog)
+            out: List[Optional[List[DocumentChunk]]] = [None] * len(batch)
+            live = []
+            for i, r in enumerate(batch):
+                visible, words = self.catalog.allow_words(r.doc_ids, r.app_id) if n else (False, None)
+                if not visible:
+                    out[i] = []
+                else:
+                    live.append((i, r, words))
+            if live:
+                kk = min(max(r.k for _, r, _ in live), n, 4096)
+                queries = [r.q for _, r, _ in live]
+                masks = [w for _, _, w in live]
+                if self._two_stage is None and hasattr(self._index, "search_host_masked") and len(live) > 1:
+                    ts, ti, tc = self._index.search_host_masked(queries, kk, masks)
+                else:  # two-stage search / injected test index: one call per distinct mask
+                    ts = np.full((len(live), kk), -np.inf, dtype=np.float32)
+                    ti = np.full((len(live), kk), -1, dtype=np.int64)
+                    tc = np.zeros((len(live),), dtype=np.int32)
+                    groups: Dict[Optional[bytes], List[int]] = {}
+                    for j, w in enumerate(masks):
+                        groups.setdefault(None if w is None else w.tobytes(), []).append(j)
+                    for idxs in groups.values():
+                        a, b, c = self._search_unlocked([queries[j] for j in idxs], kk, masks[idxs[0]])
+                        ts[idxs], ti[idxs], tc[idxs] = a, b, c
+                for row, (i, r, _) in enumerate(live):
+                    out[i] = self._chunks(ts[row], ti[row], min(int(tc[row]), r.k))
+        self.last_coalesced_batch = len(batch)
+        self.last_query_timing = {"coalesced_queries": float(len(batch)), "total_ms": (time.perf_counter() - t0) * 1e3}
+        return out  # type: ignore[return-value]
+
+    def _chunks(self, scores, ids, count: int, min_score: Optional[float] = None) -> List[DocumentChunk]:
+        hits = []
+        for j in range(count):
+            if min_score is not None and float(scores[j]) < min_score:
+                break  # sorted by score descending
+            rec = self.catalog.records[int(ids[j])]
+            hits.append(DocumentChunk(document_id=rec.document_id, chunk_number=rec.chunk_number, content=rec.content,
+                                      embedding=[], metadata=dict(rec.metadata), score=float(scores[j])))
+        return hits
 
     async def query_similar_batch(self, query_embeddings: Sequence[Any], k: int, doc_ids: Optional[List[str]] = None,
                                   app_id: Optional[str] = None, skip_image_content: bool = False,
@@ -193,24 +306,14 @@ class B200MultiVectorStore(BaseVectorStore):
         queries = [as_query_matrix(q) for q in query_embeddings]
         if len(self.catalog) == 0 or k <= 0:
             return [[] for _ in queries]
-        mask = self.catalog.allow_mask(doc_ids, app_id)
-        if mask is not None and not mask.any():
+        visible, words = self.catalog.allow_words(doc_ids, app_id)
+        if not visible:
             return [[] for _ in queries]
-        words = None if mask is None else PageCatalog.mask_words(mask)
         kk = min(int(k), len(self.catalog), 4096)
         t1 = time.perf_counter()
         ts, ti, tc = await asyncio.to_thread(self._search_locked, queries, kk, words)
         t2 = time.perf_counter()
-        out: List[List[DocumentChunk]] = []
-        for qi in range(len(queries)):
-            hits = []
-            for j in range(int(tc[qi])):
-                if min_score is not None and float(ts[qi, j]) < min_score:
-                    break  # sorted by score descending
-                rec = self.catalog.records[int(ti[qi, j])]
-                hits.append(DocumentChunk(document_id=rec.document_id, chunk_number=rec.chunk_number, content=rec.content,
-                                          embedding=[], metadata=dict(rec.metadata), score=float(ts[qi, j])))
-            out.append(hits)
+        out = [self._chunks(ts[qi], ti[qi], int(tc[qi]), min_score) for qi in range(len(queries))]
         t3 = time.perf_counter()
         self.last_query_timing = {"prepare_ms": (t1 - t0) * 1e3, "gpu_search_ms": (t2 - t1) * 1e3,
                                   "build_chunks_ms": (t3 - t2) * 1e3, "total_ms": (t3 - t0) * 1e3}
@@ -219,9 +322,12 @@ class B200MultiVectorStore(BaseVectorStore):
 
     def _search_locked(self, queries, k, words):
         with self._lock:
-            if self._two_stage is not None:
-                return self._two_stage.search(queries, k, n_candidates=max(int(self.fde_candidates), k), allow_mask=words)
-            return self._index.search_host(queries, k, allow_mask=words)
+            return self._search_unlocked(queries, k, words)
+
+    def _search_unlocked(self, queries, k, words):
+        if self._two_stage is not None:
+            return self._two_stage.search(queries, k, n_candidates=max(int(self.fde_candidates), k), allow_mask=words)
+        return self._index.search_host(queries, k, allow_mask=words)
 
     async def get_chunks_by_id(self, chunk_identifiers: List[Tuple[str, int]], app_id: Optional[str] = None,
                                skip_image_content: bool = False) -> List[DocumentChunk]:

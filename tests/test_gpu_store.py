@@ -138,6 +138,54 @@ def test_device_tensor_ingest_fast_path_matches_host_ingest(mode):
     dev.close(); host.close()
 
 
+@pytest.mark.parametrize("mode", ["bf16", "binary", "int8"])
+def test_per_query_masks_equal_individual_searches(mode):
+    """b200ms_search_host_masked: one pass, one allow-mask per query == the same queries searched one by one."""
+    from morphik_core_b200.catalog import PageCatalog
+    from morphik_core_b200.index import MaxSimIndex
+
+    rng = np.random.default_rng(31)
+    idx = MaxSimIndex(dtype=mode)
+    pages = [rng.standard_normal((int(rng.integers(5, 90)), 128)).astype(np.float32) for _ in range(300)]
+    idx.add_pages(pages)
+    queries = [rng.standard_normal((int(rng.integers(4, 40)), 128)).astype(np.float32) for _ in range(11)]
+    masks = []
+    for i in range(11):
+        if i % 4 == 0:
+            masks.append(None)
+        else:
+            m = rng.random(300) < (0.02 if i % 4 == 1 else 0.5)
+            masks.append(PageCatalog.mask_words(m))
+    masks[5] = masks[3]  # shared filter: uploaded once
+    ts, ti, tc = idx.search_host_masked(queries, 7, masks)
+    for i, (q, m) in enumerate(zip(queries, masks)):
+        s1, i1, c1 = idx.search_host([q], 7, allow_mask=m)
+        assert tc[i] == c1[0] and np.array_equal(ti[i], i1[0]) and np.array_equal(ts[i], s1[0]), i
+    with pytest.raises(ValueError):
+        idx.search_host_masked(queries, 7, masks[:3])
+
+
+def test_coalesced_concurrent_queries_use_per_query_masks():
+    """The store coalesces concurrent query_similar calls with different doc_ids into one masked GPU pass."""
+    store = B200MultiVectorStore(mode="bf16")
+    rng = np.random.default_rng(8)
+    pages = [rng.standard_normal((int(rng.integers(10, 80)), 128)).astype(np.float32) for _ in range(120)]
+    run(store.store_embeddings([DocumentChunk(document_id=f"d{i % 30}", content="", embedding=p, chunk_number=i // 30)
+                                for i, p in enumerate(pages)]))
+    reqs = [dict(query_embedding=pages[i][:12], k=2 + i % 4, doc_ids=None if i % 5 == 0 else [f"d{j}" for j in range(i % 30 + 1)])
+            for i in range(20)]
+    lone = [run(store.query_similar(**r)) for r in reqs]
+
+    async def many():
+        return await asyncio.gather(*[store.query_similar(**r) for r in reqs])
+
+    together = run(many())
+    key = lambda res: [(c.document_id, c.chunk_number, c.score) for c in res]  # noqa: E731
+    assert [key(r) for r in together] == [key(r) for r in lone]
+    assert store.last_coalesced_batch == 20
+    store.close()
+
+
 def test_save_load_round_trip(tmp_path):
     store = B200MultiVectorStore(mode="bf16")
     rng = np.random.default_rng(8)

@@ -130,3 +130,44 @@ def test_as_page_matrix_host_forms():
     t = torch.ones((3, 128), dtype=torch.bfloat16)  # CPU tensor: host float32, like the reference (multi_vector_store.py:334-337)
     b = as_page_matrix(t)
     assert isinstance(b, np.ndarray) and b.dtype == np.float32 and b.shape == (3, 128)
+
+
+def test_concurrent_queries_are_coalesced_and_each_gets_its_own_filter():
+    """Concurrent query_similar coroutines (different users: different doc_ids / app_id / k) share GPU passes; every caller
+    gets exactly what a lone call returns.  (Host logic with the injected index; the CUDA per-query-mask path is covered by
+    tests/test_gpu_store.py.)"""
+    rng = np.random.default_rng(12)
+    store = B200MultiVectorStore(auto_initialize=False, index=OracleIndex())
+    calls = {"n": 0}
+    inner = store._index.search_host
+
+    def counting(queries, k, allow_mask=None):
+        calls["n"] += 1
+        return inner(queries, k, allow_mask=allow_mask)
+
+    store._index.search_host = counting
+    embs = [rng.standard_normal((int(rng.integers(3, 40)), 128)).astype(np.float32) for _ in range(30)]
+    run(store.store_embeddings([chunk(f"doc{i % 10}", i // 10, e) for i, e in enumerate(embs[:20])], app_id="a"))
+    run(store.store_embeddings([chunk(f"doc{i % 10}", i // 10, e) for i, e in enumerate(embs[20:], start=20)], app_id="b"))
+    reqs = []
+    for i in range(18):
+        q = embs[i][:8] + 0.01 * rng.standard_normal((min(8, len(embs[i])), 128)).astype(np.float32)
+        doc_ids = None if i % 3 == 0 else [f"doc{j}" for j in range(i % 10 + 1)]
+        reqs.append(dict(query_embedding=q, k=1 + i % 5, doc_ids=doc_ids, app_id=("a", "b", None)[i % 3]))
+    reqs.append(dict(query_embedding=embs[0][:4], k=3, doc_ids=["nope"], app_id=None))  # empty filter -> []
+    lone = [run(store.query_similar(**r)) for r in reqs]
+    calls["n"] = 0
+
+    async def many():
+        return await asyncio.gather(*[store.query_similar(**r) for r in reqs])
+
+    together = run(many())
+    key = lambda res: [(c.document_id, c.chunk_number, c.score) for c in res]  # noqa: E731
+    assert [key(r) for r in together] == [key(r) for r in lone]
+    assert together[-1] == [] and all(len(r) <= q["k"] for r, q in zip(together, reqs))
+    assert store.last_coalesced_batch == len(reqs)  # one batch ...
+    assert calls["n"] < len(reqs) - 1  # ... and one index call per DISTINCT filter (13 here), not one per request (19)
+    # opting out restores one call per request
+    plain = B200MultiVectorStore(auto_initialize=False, index=store._index, coalesce_queries=False)
+    plain.catalog = store.catalog
+    assert key(run(plain.query_similar(**reqs[1]))) == key(lone[1])
