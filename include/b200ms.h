@@ -154,6 +154,13 @@ int b200ms_search_device(b200ms_t* h, const void* q_dev, int src_dtype, const in
                          const uint32_t* allow_mask_dev, float i8_q_scale, float score_scale, int64_t id_base,
                          float* top_scores_dev, int64_t* top_ids_dev, int32_t* top_counts_dev, void* stream);
 
+/* b200ms_search_device with one allow-mask per query: allow_masks_dev [n_masks, ceil(n_pages/32)] and mask_index_dev
+ * [n_q] (-1 = unfiltered) are DEVICE arrays (see b200ms_search_host_masked). */
+int b200ms_search_device_masked(b200ms_t* h, const void* q_dev, int src_dtype, const int32_t* q_lens, int n_q, int k,
+                                const uint32_t* allow_masks_dev, int n_masks, const int32_t* mask_index_dev,
+                                float i8_q_scale, float score_scale, int64_t id_base, float* top_scores_dev,
+                                int64_t* top_ids_dev, int32_t* top_counts_dev, void* stream);
+
 /* MaxSim over an explicit candidate list (the "rerank" half of a two-stage search, fast_multivector_store.py:545-557):
  * cand_ids_dev = device array of n_cand page ids (-1 = unused slot).  Only those pages are scanned; ties break towards
  * the earlier candidate slot (= better first-stage rank).  Outputs as b200ms_search_device. */

@@ -63,6 +63,8 @@ def _load() -> ctypes.CDLL:
         "b200ms_search_host": (c_int, [vp, vp, i32p, c_int, c_int, vp, c_float, c_float, c_int64, vp, vp, vp]),
         "b200ms_search_host_masked": (c_int, [vp, vp, i32p, c_int, c_int, vp, c_int, i32p, c_float, c_float, c_int64, vp, vp, vp]),
         "b200ms_search_device": (c_int, [vp, vp, c_int, i32p, c_int, c_int, vp, c_float, c_float, c_int64, vp, vp, vp, vp]),
+        "b200ms_search_device_masked": (c_int, [vp, vp, c_int, i32p, c_int, c_int, vp, c_int, vp, c_float, c_float, c_int64, vp, vp,
+                                        vp, vp]),
         "b200ms_launch_count": (c_int64, [vp]),
         "b200ms_last_score_ms": (c_float, [vp]),
         "b200ms_set_tuning": (c_int, [vp, c_int64, c_int]),
@@ -88,7 +90,7 @@ EXPORTED = [
     "b200ms_version", "b200ms_device_count", "b200ms_create", "b200ms_destroy", "b200ms_last_error",
     "b200ms_padded_len", "b200ms_padded_rows", "b200ms_row_bytes", "b200ms_query_groups", "b200ms_sign_pack",
     "b200ms_pack_pages", "b200ms_set_corpus", "b200ms_corpus_pages", "b200ms_corpus_rows", "b200ms_pack_queries",
-    "b200ms_score", "b200ms_topk", "b200ms_merge_topk", "b200ms_search_host", "b200ms_search_host_masked", "b200ms_search_device",
+    "b200ms_score", "b200ms_topk", "b200ms_merge_topk", "b200ms_search_host", "b200ms_search_host_masked", "b200ms_search_device", "b200ms_search_device_masked",
     "b200ms_launch_count", "b200ms_last_score_ms", "b200ms_set_tuning", "b200ms_score_call_count",
     "b200ms_score_times_ms", "b200ms_set_option", "b200ms_rerank_device", "b200ms_fde_configure", "b200ms_fde_dim",
     "b200ms_fde_encode", "b200ms_fde_finalize", "b200ms_fde_scan", "b200ms_hamming_batch",

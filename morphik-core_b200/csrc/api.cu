@@ -562,6 +562,21 @@ B200MS_API int b200ms_search_device(b200ms_t* h, const void* q_dev, int src_dtyp
                      top_ids_dev, top_counts_dev, static_cast<cudaStream_t>(stream));
 }
 
+B200MS_API int b200ms_search_device_masked(b200ms_t* h, const void* q_dev, int src_dtype, const int32_t* q_lens, int n_q,
+                                           int k, const uint32_t* allow_masks_dev, int n_masks,
+                                           const int32_t* mask_index_dev, float i8_q_scale, float score_scale,
+                                           int64_t id_base, float* top_scores_dev, int64_t* top_ids_dev,
+                                           int32_t* top_counts_dev, void* stream) {
+  if (!h) return B200MS_EINVAL;
+  if (!src_dtype_ok(src_dtype)) return set_error(h, B200MS_EINVAL, "search_device_masked: src dtype must be F32 or BF16");
+  if (n_masks < 0 || (n_masks > 0 && (!allow_masks_dev || !mask_index_dev)))
+    return set_error(h, B200MS_EINVAL, "search_device_masked: n_masks > 0 needs the mask matrix and one index per query");
+  DeviceGuard g(h->device);
+  return search_impl(h, q_dev, src_dtype, q_lens, n_q, k, n_masks > 0 ? allow_masks_dev : nullptr, i8_q_scale, score_scale,
+                     id_base, top_scores_dev, top_ids_dev, top_counts_dev, static_cast<cudaStream_t>(stream), nullptr, 0,
+                     n_masks > 0 ? mask_index_dev : nullptr, (h->corpus.n_pages + 31) / 32);
+}
+
 static int search_host_impl(b200ms_t* h, const float* q_host, const int32_t* q_lens, int n_q, int k,
                             const uint32_t* masks_host, int n_masks, const int32_t* mask_index_host, float i8_q_scale,
                             float score_scale, int64_t id_base, float* top_scores_host, int64_t* top_ids_host,

@@ -324,8 +324,12 @@ class MaxSimIndex:
         )
 
     def search_device(self, q_dev: torch.Tensor, q_lens: Sequence[int], k: int, allow_mask_dev: Optional[torch.Tensor] = None,
-                      id_base: int = 0, out: Optional[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]] = None):
-        """Asynchronous search with device-resident queries ([sum T,128] float32|bfloat16) on torch's current stream."""
+                      id_base: int = 0, out: Optional[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]] = None,
+                      mask_index_dev: Optional[torch.Tensor] = None):
+        """Asynchronous search with device-resident queries ([sum T,128] float32|bfloat16) on torch's current stream.
+
+        ``allow_mask_dev``: one mask (int32/uint32 words) for every query, or -- with ``mask_index_dev`` (int32 [n_q], -1 =
+        unfiltered) -- a [n_masks, words] matrix with one row per distinct filter (b200ms_search_device_masked)."""
         self._attach()
         n_q = len(q_lens)
         if q_dev.dtype not in (torch.float32, torch.bfloat16) or not q_dev.is_contiguous():
@@ -335,6 +339,22 @@ class MaxSimIndex:
                    torch.empty((n_q, k), dtype=torch.int64, device=self.device),
                    torch.empty((n_q,), dtype=torch.int32, device=self.device))
         ts, ti, tc = out
+        if mask_index_dev is not None:
+            if (allow_mask_dev is None or allow_mask_dev.ndim != 2 or allow_mask_dev.shape[1] != (self.n_pages + 31) // 32
+                    or not allow_mask_dev.is_contiguous()):
+                raise ValueError("per-query masks: allow_mask_dev must be a contiguous [n_masks, ceil(n_pages/32)] word matrix")
+            if mask_index_dev.dtype != torch.int32 or mask_index_dev.numel() != n_q:
+                raise ValueError("mask_index_dev must be int32 [n_q]")
+            with torch.cuda.device(self.device):
+                self.h.check(
+                    nat.lib.b200ms_search_device_masked(
+                        self.h.ptr, _vp(q_dev), nat.BF16 if q_dev.dtype == torch.bfloat16 else nat.F32, nat.i32_array(q_lens),
+                        n_q, int(k), _vp(allow_mask_dev), int(allow_mask_dev.shape[0]), _vp(mask_index_dev),
+                        ctypes.c_float(self.i8_scale), ctypes.c_float(self.score_scale), int(id_base), _vp(ts), _vp(ti),
+                        _vp(tc), self._stream()),
+                    "b200ms_search_device_masked",
+                )
+            return ts, ti, tc
         with torch.cuda.device(self.device):
             self.h.check(
                 nat.lib.b200ms_search_device(self.h.ptr, _vp(q_dev), nat.BF16 if q_dev.dtype == torch.bfloat16 else nat.F32,

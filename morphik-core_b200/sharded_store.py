@@ -5,8 +5,9 @@ methods (core/vector_store/base_vector_store.py:7-65).  Ranks > 0 call ``worker_
 stream.  Documents are assigned to ranks whole (least-loaded rank at first sight), so the ``doc_ids`` filter and
 ``delete_chunks_by_document_id`` stay rank-local and no page data ever moves between GPUs after ingest.
 
-A query is: rank 0 broadcasts (query rows, doc_ids, app_id, k) -> every rank builds its own page mask, scans its shard and
-selects its top-k with GLOBAL ids ``(rank << 40) | local_page`` -> ONE all-gather of n_q*k*12 bytes per rank -> merge on
+Concurrent query_similar coroutines are coalesced on rank 0 (store.QueryCoalescer) into one command per GPU pass.
+A query command is: rank 0 broadcasts (query rows, k, one (doc_ids, app_id) filter PER QUERY) -> every rank builds its own
+page masks (one row per distinct filter), scans its shard and selects its top-k with GLOBAL ids ``(rank << 40) | local_page`` -> ONE all-gather of n_q*k*12 bytes per rank -> merge on
 every rank (``ShardedMaxSim``) -> rank 0 turns ids into DocumentChunks.  Rank 0 mirrors every rank's catalogue (payloads
 and metadata live only there); the catalogues evolve deterministically from the command stream, including compactions.
 
@@ -27,7 +28,7 @@ import torch.distributed as dist
 from .catalog import PageCatalog, PageRecord
 from .models import DocumentChunk
 from .sharded import ShardedMaxSim
-from .store import BaseVectorStore, as_query_matrix, build_store_metrics
+from .store import BaseVectorStore, QueryCoalescer, _QueryRequest, as_query_matrix, build_store_metrics
 
 logger = logging.getLogger(__name__)
 RANK_SHIFT = 40
@@ -37,9 +38,10 @@ def split_global_id(gid: int) -> Tuple[int, int]:
     return int(gid) >> RANK_SHIFT, int(gid) & ((1 << RANK_SHIFT) - 1)
 
 
-class ShardedB200MultiVectorStore(BaseVectorStore):
+class ShardedB200MultiVectorStore(QueryCoalescer, BaseVectorStore):
     def __init__(self, mode: str = "bf16", device: Optional[int] = None, group: Optional[dist.ProcessGroup] = None,
-                 index_factory: Optional[Callable[[], Any]] = None, compact_dead_fraction: float = 0.3):
+                 index_factory: Optional[Callable[[], Any]] = None, compact_dead_fraction: float = 0.3,
+                 coalesce_queries: bool = True, max_coalesced_tokens: int = 1024, max_coalesced_queries: int = 64):
         if not dist.is_initialized():
             raise RuntimeError("ShardedB200MultiVectorStore needs an initialised torch.distributed process group (torchrun)")
         self.group = group
@@ -60,9 +62,11 @@ class ShardedB200MultiVectorStore(BaseVectorStore):
         self.catalogs: Dict[int, PageCatalog] = {r: PageCatalog() for r in (range(self.world) if self.rank == 0 else [self.rank])}
         self.doc_rank: Dict[str, int] = {}
         self.rank_rows = [0] * self.world
-        self._lock = threading.Lock()
+        self._lock = threading.RLock()  # re-entrant: a query holds it across the command AND the catalogue look-ups
         self._sharded = ShardedMaxSim(self._local_search, self._merge, group)
-        self._mask_words: Optional[np.ndarray] = None
+        self._init_coalescer(coalesce_queries, max_coalesced_tokens, max_coalesced_queries)
+        self._mask_matrix: Optional[torch.Tensor] = None  # [n_distinct_filters, words] int32, this rank's pages
+        self._mask_index: Optional[torch.Tensor] = None   # int32 [n_q]: row of _mask_matrix per query, -1 = unfiltered
         self._skip_local = False
         self._pending_rows: Optional[np.ndarray] = None
 
@@ -84,10 +88,11 @@ class ShardedB200MultiVectorStore(BaseVectorStore):
         if self._skip_local:  # empty shard or nothing authorised here: contribute an empty list to the collective
             return (torch.full((len(q_lens), k), float("-inf"), device=self.data_device),
                     torch.full((len(q_lens), k), -1, dtype=torch.int64, device=self.data_device))
-        mask = None
-        if self._mask_words is not None:
-            mask = torch.from_numpy(self._mask_words.view(np.int32)).to(self.data_device)
-        ts, ti, _ = self.index.search_device(q, list(q_lens), k, allow_mask_dev=mask, id_base=self.rank << RANK_SHIFT)
+        if self._mask_matrix is None:
+            ts, ti, _ = self.index.search_device(q, list(q_lens), k, id_base=self.rank << RANK_SHIFT)
+        else:
+            ts, ti, _ = self.index.search_device(q, list(q_lens), k, allow_mask_dev=self._mask_matrix,
+                                                 id_base=self.rank << RANK_SHIFT, mask_index_dev=self._mask_index)
         return ts, ti
 
     def _merge(self, cand_scores, cand_ids, k):
@@ -111,14 +116,33 @@ class ShardedB200MultiVectorStore(BaseVectorStore):
                     self.catalogs[owner].add(PageRecord(doc, num, "", {}, app, n))
             return None
         if op == "query":
-            _, q_lens, k, doc_ids, app_id = cmd
+            _, q_lens, k, filters = cmd
             q = self._bcast_rows(self._pending_rows, int(sum(q_lens)))
             self._pending_rows = None
             cat = self.catalogs[self.rank]
-            mask = cat.allow_mask(doc_ids, app_id) if len(cat) else None
-            self._mask_words = None if mask is None else PageCatalog.mask_words(mask)
+            n = len(cat)
+            rows, index, seen, any_visible = [], [], {}, False
+            for doc_ids, app_id in filters:
+                visible, words = cat.allow_words(doc_ids, app_id) if n else (False, None)
+                if not visible:  # nothing authorised on this rank: an all-zero mask keeps the query out of the local top-k
+                    words = np.zeros((n + 31) // 32, dtype=np.uint32)
+                else:
+                    any_visible = True
+                if words is None:
+                    index.append(-1)
+                    continue
+                key = words.tobytes()
+                if key not in seen:
+                    seen[key] = len(rows)
+                    rows.append(words)
+                index.append(seen[key])
+            self._skip_local = n == 0 or not any_visible
+            if rows and not self._skip_local:
+                self._mask_matrix = torch.from_numpy(np.stack(rows).view(np.int32)).to(self.data_device)
+                self._mask_index = torch.tensor(index, dtype=torch.int32, device=self.data_device)
+            else:
+                self._mask_matrix = self._mask_index = None
             kk = max(1, min(int(k), 4096))
-            self._skip_local = len(cat) == 0 or (mask is not None and not mask.any())
             return self._sharded.search(q, q_lens, kk)
         if op == "delete":
             _, document_id = cmd
@@ -197,14 +221,27 @@ class ShardedB200MultiVectorStore(BaseVectorStore):
         q = as_query_matrix(query_embedding)
         if k <= 0 or all(len(c) == 0 for c in self.catalogs.values()):
             return []
-        ts, ti, tc = await asyncio.to_thread(self._drive, ("query", [int(q.shape[0])], int(k), doc_ids, app_id), q)
-        ts, ti, n = ts[0].cpu().numpy(), ti[0].cpu().numpy(), int(tc[0])
+        if self.coalesce_queries:
+            return await self._enqueue_query(q, k, doc_ids, app_id)
+        return (await asyncio.to_thread(self._search_coalesced_locked, [_QueryRequest(q, int(k), doc_ids, app_id, None)]))[0]
+
+    def _search_coalesced_locked(self, batch) -> List[List[DocumentChunk]]:
+        """One command (= one pass on every GPU) for a batch of independent requests."""
+        q_lens = [int(r.q.shape[0]) for r in batch]
+        kmax = max(r.k for r in batch)
+        rows = np.concatenate([r.q for r in batch]) if len(batch) > 1 else batch[0].q
         out = []
-        for j in range(min(n, int(k))):
-            r, local = split_global_id(ti[j])
-            rec = self.catalogs[r].records[local]
-            out.append(DocumentChunk(document_id=rec.document_id, chunk_number=rec.chunk_number, content=rec.content,
-                                     embedding=[], metadata=dict(rec.metadata), score=float(ts[j])))
+        with self._lock:
+            ts, ti, tc = self._drive(("query", q_lens, kmax, [(r.doc_ids, r.app_id) for r in batch]), rows)
+            ts, ti, tc = ts.cpu().numpy(), ti.cpu().numpy(), tc.cpu().numpy()
+            for i, r in enumerate(batch):
+                hits = []
+                for j in range(min(int(tc[i]), r.k)):
+                    rk, local = split_global_id(ti[i, j])
+                    rec = self.catalogs[rk].records[local]
+                    hits.append(DocumentChunk(document_id=rec.document_id, chunk_number=rec.chunk_number, content=rec.content,
+                                              embedding=[], metadata=dict(rec.metadata), score=float(ts[i, j])))
+                out.append(hits)
         return out
 
     async def get_chunks_by_id(self, chunk_identifiers: List[Tuple[str, int]], app_id: Optional[str] = None,

@@ -123,7 +123,58 @@ class _LoopQueue:
         self.task = None
 
 
-class B200MultiVectorStore(BaseVectorStore):
+class QueryCoalescer:
+    """Mixin: concurrent ``query_similar`` coroutines share GPU passes.  The host class provides
+    ``_search_coalesced_locked(batch) -> List[List[DocumentChunk]]`` (runs in a worker thread) and calls
+    ``_init_coalescer`` in its constructor."""
+
+    def _init_coalescer(self, coalesce_queries: bool, max_coalesced_tokens: int, max_coalesced_queries: int) -> None:
+        # 1024 tokens = one CTA-pair pass over the corpus
+        self.coalesce_queries = bool(coalesce_queries)
+        self.max_coalesced_tokens = int(max_coalesced_tokens)
+        self.max_coalesced_queries = int(max_coalesced_queries)
+        self._queues: "weakref.WeakKeyDictionary[Any, _LoopQueue]" = weakref.WeakKeyDictionary()
+        self._queues_lock = threading.Lock()
+        self.last_coalesced_batch = 0
+
+    async def _enqueue_query(self, q: np.ndarray, k: int, doc_ids, app_id) -> List[DocumentChunk]:
+        loop = asyncio.get_running_loop()
+        with self._queues_lock:
+            lq = self._queues.get(loop)
+            if lq is None:
+                lq = self._queues[loop] = _LoopQueue()
+        req = _QueryRequest(q, int(k), doc_ids, app_id, loop.create_future())
+        lq.pending.append(req)
+        if lq.task is None or lq.task.done():
+            lq.task = loop.create_task(self._drain(lq))
+        return await req.future
+
+    async def _drain(self, lq: _LoopQueue) -> None:
+        """Score everything that is pending, one GPU pass per batch; requests arriving meanwhile form the next batch."""
+        while lq.pending:
+            batch, tokens = [], 0
+            while lq.pending and len(batch) < self.max_coalesced_queries:
+                nxt = lq.pending[0]
+                if batch and tokens + nxt.q.shape[0] > self.max_coalesced_tokens:
+                    break
+                batch.append(lq.pending.popleft())
+                tokens += nxt.q.shape[0]
+            try:
+                results = await asyncio.to_thread(self._search_coalesced_locked, batch)
+            except BaseException as e:  # noqa: BLE001  (every waiter must be released; errors propagate like the reference's)
+                for r in batch:
+                    if not r.future.done():
+                        r.future.set_exception(e if isinstance(e, Exception) else RuntimeError(repr(e)))
+                if not isinstance(e, Exception):
+                    raise
+                continue
+            self.last_coalesced_batch = len(batch)
+            for r, res in zip(batch, results):
+                if not r.future.done():
+                    r.future.set_result(res)
+
+
+class B200MultiVectorStore(QueryCoalescer, BaseVectorStore):
     """Exhaustive ColPali MaxSim store on one B200 (see module docstring)."""
 
     def __init__(self, uri: str = "b200://0", device: int = 0, mode: str = "bf16", storage: Any = None,
@@ -141,13 +192,7 @@ class B200MultiVectorStore(BaseVectorStore):
         # the "morphik" provider -- FDE candidates (the reference asks Turbopuffer for min(10*k, 75)) then MaxSim rerank.
         self.fde_candidates = fde_candidates
         self._two_stage = None
-        # concurrent query_similar calls share GPU passes (see module docstring); 1024 tokens = one CTA-pair pass
-        self.coalesce_queries = bool(coalesce_queries)
-        self.max_coalesced_tokens = int(max_coalesced_tokens)
-        self.max_coalesced_queries = int(max_coalesced_queries)
-        self._queues: "weakref.WeakKeyDictionary[Any, _LoopQueue]" = weakref.WeakKeyDictionary()
-        self._queues_lock = threading.Lock()
-        self.last_coalesced_batch = 0
+        self._init_coalescer(coalesce_queries, max_coalesced_tokens, max_coalesced_queries)  # see module docstring
         self._lock = threading.Lock()
         self._last_store_metrics: Dict[str, Any] = {}
         self.last_query_timing: Dict[str, float] = {}
@@ -216,39 +261,7 @@ class B200MultiVectorStore(BaseVectorStore):
         q = as_query_matrix(query_embedding)
         if k <= 0:
             return []
-        loop = asyncio.get_running_loop()
-        with self._queues_lock:
-            lq = self._queues.get(loop)
-            if lq is None:
-                lq = self._queues[loop] = _LoopQueue()
-        req = _QueryRequest(q, int(k), doc_ids, app_id, loop.create_future())
-        lq.pending.append(req)
-        if lq.task is None or lq.task.done():
-            lq.task = loop.create_task(self._drain(lq))
-        return await req.future
-
-    async def _drain(self, lq: _LoopQueue) -> None:
-        """Score everything that is pending, one GPU pass per batch; requests arriving meanwhile form the next batch."""
-        while lq.pending:
-            batch, tokens = [], 0
-            while lq.pending and len(batch) < self.max_coalesced_queries:
-                nxt = lq.pending[0]
-                if batch and tokens + nxt.q.shape[0] > self.max_coalesced_tokens:
-                    break
-                batch.append(lq.pending.popleft())
-                tokens += nxt.q.shape[0]
-            try:
-                results = await asyncio.to_thread(self._search_coalesced_locked, batch)
-            except BaseException as e:  # noqa: BLE001  (every waiter must be released; errors propagate like the reference's)
-                for r in batch:
-                    if not r.future.done():
-                        r.future.set_exception(e if isinstance(e, Exception) else RuntimeError(repr(e)))
-                if not isinstance(e, Exception):
-                    raise
-                continue
-            for r, res in zip(batch, results):
-                if not r.future.done():
-                    r.future.set_result(res)
+        return await self._enqueue_query(q, k, doc_ids, app_id)
 
     def _search_coalesced_locked(self, batch: List[_QueryRequest]) -> List[List[DocumentChunk]]:
         """One pass for a batch of independent requests; masks are built under the lock so they match the corpus."""
@@ -281,7 +294,6 @@ class B200MultiVectorStore(BaseVectorStore):
                         ts[idxs], ti[idxs], tc[idxs] = a, b, c
                 for row, (i, r, _) in enumerate(live):
                     out[i] = self._chunks(ts[row], ti[row], min(int(tc[row]), r.k))
-        self.last_coalesced_batch = len(batch)
         self.last_query_timing = {"coalesced_queries": float(len(batch)), "total_ms": (time.perf_counter() - t0) * 1e3}
         return out  # type: ignore[return-value]
 

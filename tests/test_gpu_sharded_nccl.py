@@ -126,6 +126,20 @@ def _store_worker(rank, world, port, result_dir):
         on1 = [d for d, r in store.doc_rank.items() if r == 1][:3]
         res = run(store.query_similar(q, k=50, doc_ids=on1))
         assert [(r.document_id, r.chunk_number) for r in res] == oracle(q, 50, set(on1))[0]
+        # concurrent callers, different filters: one coalesced command, per-query masks on every GPU
+        on0 = [d for d, r in store.doc_rank.items() if r == 0][:2]
+        reqs = [dict(query_embedding=q, k=10), dict(query_embedding=q, k=50, doc_ids=on1), dict(query_embedding=q, k=4, doc_ids=on0),
+                dict(query_embedding=docs["doc3"][0][:20], k=5, doc_ids=on0 + on1), dict(query_embedding=q, k=3, doc_ids=["nope"])]
+
+        async def many():
+            return await asyncio.gather(*[store.query_similar(**r) for r in reqs])
+
+        together = run(many())
+        assert store.last_coalesced_batch == len(reqs) and together[4] == []
+        assert [(r.document_id, r.chunk_number) for r in together[0]] == want
+        assert [(r.document_id, r.chunk_number) for r in together[1]] == oracle(q, 50, set(on1))[0]
+        assert [(r.document_id, r.chunk_number) for r in together[2]] == oracle(q, 4, set(on0))[0]
+        assert [(r.document_id, r.chunk_number) for r in together[3]] == oracle(docs["doc3"][0][:20], 5, set(on0 + on1))[0]
         for d in list(docs)[:7]:
             run(store.delete_chunks_by_document_id(d))
             docs.pop(d)

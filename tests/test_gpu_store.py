@@ -163,6 +163,21 @@ def test_per_query_masks_equal_individual_searches(mode):
         assert tc[i] == c1[0] and np.array_equal(ti[i], i1[0]) and np.array_equal(ts[i], s1[0]), i
     with pytest.raises(ValueError):
         idx.search_host_masked(queries, 7, masks[:3])
+    # the device form (what every rank of the sharded store calls): mask matrix + row index per query
+    rows, index = [], []
+    for m in masks:
+        if m is None:
+            index.append(-1)
+        else:
+            index.append(next((j for j, r in enumerate(rows) if np.array_equal(r, m)), len(rows)))
+            if index[-1] == len(rows):
+                rows.append(m)
+    mm = torch.from_numpy(np.stack(rows).view(np.int32)).cuda()
+    mi = torch.tensor(index, dtype=torch.int32).cuda()
+    q_dev = torch.from_numpy(np.concatenate(queries)).cuda()
+    ds, di, dc = idx.search_device(q_dev, [len(q) for q in queries], 7, allow_mask_dev=mm, mask_index_dev=mi)
+    torch.cuda.synchronize()
+    assert np.array_equal(ds.cpu().numpy(), ts) and np.array_equal(di.cpu().numpy(), ti) and np.array_equal(dc.cpu().numpy(), tc)
 
 
 def test_coalesced_concurrent_queries_use_per_query_masks():

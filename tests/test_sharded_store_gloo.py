@@ -31,21 +31,29 @@ class OracleShardIndex:
     def compact(self, keep):
         self.pages = [self.pages[int(i)] for i in keep]
 
-    def search_device(self, q, q_lens, k, allow_mask_dev=None, id_base=0):
+    def search_device(self, q, q_lens, k, allow_mask_dev=None, id_base=0, mask_index_dev=None):
         lens = [len(p) for p in self.pages]
         rows = np.concatenate(self.pages) if sum(lens) else np.zeros((0, 128), np.float32)
         off = orc.page_offsets(lens)
-        allow = None
-        if allow_mask_dev is not None:
+
+        def allow_of(i):  # one mask for everybody, or a row of the mask matrix per query (-1 = unfiltered)
+            if allow_mask_dev is None:
+                return None
             words = allow_mask_dev.numpy().view(np.uint32)
-            allow = np.unpackbits(words.view(np.uint8), bitorder="little")[: len(lens)].astype(bool)
+            if mask_index_dev is not None:
+                mi = int(mask_index_dev[i])
+                if mi < 0:
+                    return None
+                words = words[mi]
+            return np.unpackbits(np.ascontiguousarray(words).view(np.uint8), bitorder="little")[: len(lens)].astype(bool)
+
         ts = torch.full((len(q_lens), k), float("-inf"))
         ti = torch.full((len(q_lens), k), -1, dtype=torch.int64)
         tc = torch.zeros(len(q_lens), dtype=torch.int32)
         qo = np.concatenate([[0], np.cumsum(q_lens)])
         for i in range(len(q_lens)):
             s = orc.float_maxsim_c(q[qo[i]:qo[i + 1]].numpy(), rows, off)
-            a, b = orc.topk_np(s, k, allow)
+            a, b = orc.topk_np(s, k, allow_of(i))
             ts[i, :len(a)] = torch.from_numpy(a.astype(np.float32))
             ti[i, :len(b)] = torch.from_numpy(b + id_base)
             tc[i] = len(a)
@@ -116,6 +124,20 @@ def _worker(rank, world, port, out_dir):
         assert {r.document_id for r in res} <= set(some) and [(r.document_id, r.chunk_number) for r in res] == oracle(q, 20, set(some))[0]
         assert run(store.query_similar(q, k=5, doc_ids=["nope"])) == []
         assert run(store.query_similar(q, k=5, app_id="other")) == []
+        # concurrent callers with different filters and k share ONE command (one pass per rank) and get their own answers
+        on0 = [d for d in docs if owners[d] == 0][:2]
+        reqs = [dict(query_embedding=q, k=6), dict(query_embedding=q, k=20, doc_ids=some), dict(query_embedding=q, k=3, doc_ids=on0),
+                dict(query_embedding=docs["doc1"][0], k=4, doc_ids=some + on0), dict(query_embedding=q, k=5, doc_ids=["nope"]),
+                dict(query_embedding=q, k=2, app_id="app")]
+        lone = [run(store.query_similar(**r)) for r in reqs]
+
+        async def many():
+            return await asyncio.gather(*[store.query_similar(**r) for r in reqs])
+
+        together = run(many())
+        key = lambda rs: [(r.document_id, r.chunk_number, r.score) for r in rs]  # noqa: E731
+        assert [key(r) for r in together] == [key(r) for r in lone] and together[4] == [] and store.last_coalesced_batch == len(reqs)
+        assert [(r.document_id, r.chunk_number) for r in together[2]] == oracle(q, 3, set(on0))[0]
         # deletes (with compaction on the owning rank) keep results identical to the oracle over the survivors
         for d in ("doc7", "doc2", "doc3", "doc9", "doc11"):
             assert run(store.delete_chunks_by_document_id(d)) is True
