@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define B200MS_VERSION 100 /* 0.1.0 */
+#define B200MS_VERSION 101 /* 0.1.1: + b200ms_search_host_masked, b200ms_search_device_masked, option "pair_cta" */
 
 /* element types */
 #define B200MS_F32 0  /* float32 source rows (ingest / query side only)            */

@@ -12,4 +12,4 @@ include/b200ms.h (ctypes).  Modules:
   shardfile packed shard files (the HBM layout on disk) + importers for the reference's .npy / BIT(128)[] forms
   reranker  embedding-based MaxSim reranker adapter
 """
-__version__ = "0.1.0"
+__version__ = "0.1.1"

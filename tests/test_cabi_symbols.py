@@ -46,7 +46,7 @@ def test_layout_helpers():
     from morphik_core_b200 import _native as nat
 
     lib = nat.lib
-    assert lib.b200ms_version() == 100
+    assert lib.b200ms_version() == 101
     assert [lib.b200ms_padded_len(n) for n in (0, 1, 31, 32, 33, 1024, 1030)] == [0, 32, 32, 32, 64, 1024, 1056]
     lens = nat.i32_array([0, 1, 32, 33, 1024])
     assert lib.b200ms_padded_rows(lens, 5) == 0 + 32 + 32 + 64 + 1024
