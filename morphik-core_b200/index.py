@@ -192,6 +192,12 @@ class MaxSimIndex:
                          "b200ms_set_corpus")
         self._attached = True
 
+    def clear(self):
+        """Drop every page but keep the device buffer and the native handle (scratch indexes, e.g. the reranker's)."""
+        self._rows = 0
+        self._page_lens = []
+        self._attached = False
+
     def compact(self, keep: Sequence[int]):
         """Keep only the pages in `keep` (ascending old ids), renumbering them 0..len(keep)-1: device-to-device copies of
         the surviving page runs into a fresh buffer (DELETE ... WHERE document_id, multi_vector_store.py:929-933)."""

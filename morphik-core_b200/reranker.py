@@ -8,26 +8,38 @@ query's multivector: "retrieve with any store, rerank with ColPali MaxSim on the
 """
 from __future__ import annotations
 
+import threading
 from typing import List, Optional, Sequence, Union
 
 import numpy as np
 
 from .index import MaxSimIndex
 from .models import DocumentChunk
-from .store import as_query_matrix
+from .store import as_page_matrix, as_query_matrix
 
 
 class B200MaxSimReranker:
     def __init__(self, device: int = 0, mode: str = "bf16"):
         self.device, self.mode = int(device), mode
+        self._idx: Optional[MaxSimIndex] = None
+        self._lock = threading.Lock()
 
     def _scores(self, query_embedding, page_embeddings: Sequence) -> np.ndarray:
-        idx = MaxSimIndex(device=self.device, dtype=self.mode)
-        try:
-            idx.add_pages([np.asarray(e, dtype=np.float32).reshape(-1, 128) for e in page_embeddings])
+        """One scratch index is reused across calls (its device buffer and native handle stay); candidate embeddings may be
+        host arrays / lists or CUDA tensors (those stay on the device, store.as_page_matrix)."""
+        with self._lock:
+            if self._idx is None:
+                self._idx = MaxSimIndex(device=self.device, dtype=self.mode)
+            idx = self._idx
+            idx.clear()
+            idx.add_pages([as_page_matrix(e) for e in page_embeddings])
             return idx.score_matrix([as_query_matrix(query_embedding)])[0]
-        finally:
-            idx.close()
+
+    def close(self) -> None:
+        with self._lock:
+            if self._idx is not None:
+                self._idx.close()
+                self._idx = None
 
     async def rerank(self, query_embedding, chunks: List[DocumentChunk], min_score: Optional[float] = None
                      ) -> List[DocumentChunk]:
