@@ -29,7 +29,7 @@ import logging
 import threading
 import time
 import weakref
-from typing import Any, Dict, List, Optional, Sequence, Tuple, Union
+from typing import Any, Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
 
