@@ -230,6 +230,32 @@ def config0_latency(packed, q_pin, out_pin, k, skip_cpu, n_pages=100, iters=300)
     return out
 
 
+def topk_match_vs_oracle(packed, q_pin, n_q, k, n_pages=512, n_queries=4):
+    """Top-k lists of b200ms_search_host on the first n_pages of the shard vs the CPU oracle (fp32 MaxSim on the same
+    bf16-valued inputs): identical id lists and the largest relative score difference.  Checker only (oracle/)."""
+    import numpy as np
+    import torch
+
+    from morphik_core_b200.index import MaxSimIndex
+    from oracle import maxsim_oracle as orc
+
+    nq = min(n_q, n_queries)
+    sub = MaxSimIndex(device=packed.device.index or 0, dtype="bf16")
+    sub.adopt_packed(packed[: n_pages * P_PATCH * DIM * 2], [P_PATCH] * n_pages)
+    queries = [q_pin[i * T_TOK:(i + 1) * T_TOK].numpy() for i in range(nq)]
+    ts, ti, tc = sub.search_host(queries, k)
+    rows = packed[: n_pages * P_PATCH * DIM * 2].view(torch.bfloat16).view(-1, DIM).float().cpu().numpy()
+    off = orc.page_offsets([P_PATCH] * n_pages)
+    same, err = 0, 0.0
+    for i, q in enumerate(queries):
+        want = orc.float_maxsim_c(orc.bf16_round_np(q), rows, off)
+        ws, wi = orc.topk_np(want, k)
+        same += int(ti[i].tolist() == wi.tolist())
+        err = max(err, float(np.max(np.abs(ts[i] - ws) / np.maximum(np.abs(ws), 1e-6))))
+    return {"sample": f"first {n_pages} pages of the shard, {nq} queries, top-{k}", "id_lists_identical": f"{same}/{nq}",
+            "max_rel_score_err": err, "tolerance": 1e-3}
+
+
 def torch_gpu_reference_rate(rows_bf16, q_dev, n_q, sample_pages=4096, iters=5):
     """The kernel-to-beat on the same GPU: the reference's OWN GPU formulation -- colpali_engine
     score_multi_vector with device="cuda" (fast_multivector_store.py:339,553-555) = einsum("bnd,csd->bcns").max(3).sum(2)
@@ -495,6 +521,11 @@ def run_gpu(args):
         cpu = {"value": r["value"], "unit": UNIT, "cores": r["threads"], "kind": "port", "host_cpus": os.cpu_count(),
                "sample": f"{r['pages']} pages x {P_PATCH} patches x {DIM}-d, {n_q} queries x {T_TOK} tokens, "
                          f"{r['seconds']:.1f} s of score_multi_vector (torch einsum, fp32) on the host"}
+
+        try:  # "top-k match vs reference" (BASELINE metric): the C-ABI path against the oracle on a sample of the shard
+            cpu["topk_match"] = topk_match_vs_oracle(packed, q_pin, n_q, k)
+        except Exception as e:  # noqa: BLE001
+            cpu["topk_match"] = {"error": repr(e)[:200]}
 
     if rank == 0:
         line = {
