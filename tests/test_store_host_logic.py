@@ -171,3 +171,47 @@ def test_concurrent_queries_are_coalesced_and_each_gets_its_own_filter():
     plain = B200MultiVectorStore(auto_initialize=False, index=store._index, coalesce_queries=False)
     plain.catalog = store.catalog
     assert key(run(plain.query_similar(**reqs[1]))) == key(lone[1])
+
+
+def test_allow_words_cache_follows_catalogue_mutations():
+    """The mask LRU is keyed by the catalogue version: adds, deletes and compaction never serve a stale filter."""
+    c = PageCatalog()
+    for i in range(70):
+        c.add(PageRecord(f"d{i % 7}", i // 7, "", {}, "a" if i % 2 else None, 5))
+    vis, w = c.allow_words(["d1", "d3"], None)
+    assert vis and w.shape == (3,) and np.array_equal(w, PageCatalog.mask_words(c.allow_mask(["d1", "d3"], None)))
+    assert c.allow_words(["d1", "d3"], None)[1] is w  # LRU hit returns the cached array
+    assert c.allow_words(None, None) == (True, None)  # nothing filtered: no mask upload
+    assert c.allow_words(["nope"], None)[0] is False
+    # app_id: pages stored under another app are hidden, pages without one stay visible
+    m = c.allow_mask(None, "b")
+    assert m is not None and m.sum() == 35 and not m[1]
+    c.add(PageRecord("d1", 99, "", {}, None, 5))  # mutation -> new version -> recomputed, now 71 pages
+    vis2, w2 = c.allow_words(["d1", "d3"], None)
+    assert w2 is not w and np.array_equal(w2, PageCatalog.mask_words(c.allow_mask(["d1", "d3"], None))) and (w2[2] >> 6) & 1
+    c.delete_document("d3")
+    m3 = c.allow_mask(["d1", "d3"], None)
+    assert np.array_equal(c.allow_words(["d1", "d3"], None)[1], PageCatalog.mask_words(m3)) and m3.sum() == 11
+    keep, _ = c.compaction_plan()
+    c.apply_compaction(keep)
+    assert len(c) == 61 and c.allow_mask(["d3"], None).sum() == 0
+    assert np.array_equal(c.allow_words(["d1"], None)[1], PageCatalog.mask_words(c.allow_mask(["d1"], None)))
+
+
+def test_coalesced_query_errors_reach_every_waiter():
+    class Boom(OracleIndex):
+        def search_host(self, queries, k, allow_mask=None):
+            raise RuntimeError("device lost")
+
+    store = B200MultiVectorStore(auto_initialize=False, index=Boom())
+    run(store.store_embeddings([chunk("d", 0, np.ones((3, 128)))]))
+
+    async def many():
+        return await asyncio.gather(*[store.query_similar(np.ones((2, 128)), k=1) for _ in range(3)], return_exceptions=True)
+
+    res = run(many())
+    assert len(res) == 3 and all(isinstance(r, RuntimeError) and "device lost" in str(r) for r in res)
+    # the queue recovers: a later healthy call works
+    store._index = OracleIndex()
+    store._index.add_pages([np.ones((3, 128), np.float32)])
+    assert [r.document_id for r in run(store.query_similar(np.ones((2, 128)), k=1))] == ["d"]
