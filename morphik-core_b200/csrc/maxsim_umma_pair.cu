@@ -18,7 +18,8 @@
 //     tiles m with m % 2 == e>>1 -- exactly the W4 epilogue of maxsim_umma.cu per (accumulator, half).
 //   * barriers: full[s] lives in the leader (both producers' TMA bytes land on it), empty[s] / tfull[b] are arrived in
 //     both CTAs by multicast tcgen05.commit, tempty[b] lives in the leader and collects 16 warp arrivals (8 remote).
-// Used when a pass has >= 3 query tiles (> 256 query tokens); smaller batches are HBM-bound and stay on maxsim_umma.cu.
+// Used for passes of >= 2 query tiles (> 128 query tokens; the two-tile form is maxsim_umma_pair1_kernel below); a single
+// tile (<= 128 tokens, the lone-query case) is HBM-bound and stays on maxsim_umma.cu.  Pass planning: launch_kind().
 #include "common.cuh"
 #include "ptx.cuh"
 #include "umma_tile.cuh"
