@@ -41,7 +41,9 @@
 extern "C" {
 #endif
 
-#define B200MS_VERSION 101 /* 0.1.1: + b200ms_search_host_masked, b200ms_search_device_masked, option "pair_cta" */
+#define B200MS_VERSION 200 /* 0.2.0: + multi-GPU entry points (b200ms_comm_*, b200ms_allgather_topk, b200ms_sharded_search_*),
+                              b200ms_rerank_batch_device, b200ms_fde_configure_ex, B200MS_F8 corpora, option "zero_pad_compat";
+                              options "a_in_tmem" / "split4" / "epi_w4" removed with the kernels they selected */
 
 /* element types */
 #define B200MS_F32 0  /* float32 source rows (ingest / query side only)            */
@@ -49,6 +51,7 @@ extern "C" {
 #define B200MS_I8 2   /* int8 rows, 128 B per patch vector (global symmetric scale) */
 #define B200MS_B1 3   /* sign bits, MSB-first, 16 B per patch vector                */
 #define B200MS_I32 4  /* int32 scores (I8 / B1 corpora)                             */
+#define B200MS_F8 5   /* fp8 e4m3 rows, 128 B per patch vector (global power-of-two scale), f32 scores */
 
 /* error codes */
 #define B200MS_OK 0
@@ -75,7 +78,7 @@ const char* b200ms_last_error(const b200ms_t* h);
 int64_t b200ms_padded_len(int64_t len);
 /* Sum of b200ms_padded_len over page_lens[0..n_pages). */
 int64_t b200ms_padded_rows(const int32_t* page_lens, int64_t n_pages);
-/* Bytes per row for a corpus dtype (256 / 128 / 16), or 0. */
+/* Bytes per row for a corpus dtype (BF16 256 / I8 and F8 128 / B1 16), or 0. */
 int64_t b200ms_row_bytes(int dtype);
 /* Number of 32-row query groups for queries of the given lengths: sum ceil(len/32) (a 0-length query -> 0). */
 int64_t b200ms_query_groups(const int32_t* q_lens, int n_q);
@@ -91,12 +94,13 @@ int b200ms_hamming_batch(b200ms_t* h, const uint8_t* q_bits, const uint8_t* cand
 /* Convert n_pages pages stored back to back at src (device, [sum len,128] F32|BF16) into the padded
  * corpus layout at dst (device): page i occupies padded_len(len_i) rows, the padding rows repeat the
  * page's last true row (max-/min-invariant, so scores are unchanged).  dst_dtype BF16: round-to-nearest-even;
- * I8: rint(x * i8_scale) clamped to [-127,127]; B1: sign bits.  page_lens is a HOST array. */
+ * I8: rint(x * i8_scale) clamped to [-127,127]; F8: e4m3(x * i8_scale), round-to-nearest-even, saturating (use a power-of-two
+ * scale, 64 for unit-norm rows); B1: sign bits.  page_lens is a HOST array. */
 int b200ms_pack_pages(b200ms_t* h, const void* src, int src_dtype, const int32_t* page_lens, int64_t n_pages,
                       void* dst, int dst_dtype, float i8_scale, void* stream);
 
 /* Attach a packed corpus (device memory, caller-owned, must stay valid until the next set_corpus/destroy).
- * rows: [b200ms_padded_rows(page_lens), 128] of dtype BF16|I8|B1, 1024-byte aligned.  page_lens (HOST) are the
+ * rows: [b200ms_padded_rows(page_lens), 128] of dtype BF16|I8|F8|B1, 1024-byte aligned.  page_lens (HOST) are the
  * TRUE lengths.  Builds the chunk->page table, the work-unit plan and the TMA descriptor. */
 int b200ms_set_corpus(b200ms_t* h, const void* rows, int dtype, const int32_t* page_lens, int64_t n_pages);
 int64_t b200ms_corpus_pages(const b200ms_t* h);
@@ -111,7 +115,7 @@ int b200ms_pack_queries(b200ms_t* h, const void* q, int src_dtype, const int32_t
 
 /* ---- the hot path ---------------------------------------------------------------------------- */
 /* group_scores[g, p] = sum over the (<=32) tokens of group g of max over the rows of page p of <q_t, d_r>
- *   BF16 corpus: float32 (fp32 accumulate on tcgen05);  I8: int32 exact;  B1: int32 sum_t max_r (128 - hamming).
+ *   BF16 / F8 corpus: float32 (fp32 accumulate on tcgen05);  I8: int32 exact;  B1: int32 sum_t max_r (128 - hamming).
  * q_packed: device [roundup(n_groups,4)*32, 128] of the corpus dtype; q_lens/group_offsets (HOST) as produced by
  * b200ms_pack_queries (B1 needs the true token counts; may be NULL for BF16/I8).
  * group_scores: device [n_groups_padded, ld] with ld >= n_pages, n_groups_padded = roundup(n_groups,4).
@@ -168,6 +172,55 @@ int b200ms_rerank_device(b200ms_t* h, const void* q_dev, int src_dtype, const in
                          const int64_t* cand_ids_dev, int n_cand, int k, float i8_q_scale, float score_scale,
                          float* top_scores_dev, int64_t* top_ids_dev, int32_t* top_counts_dev, void* stream);
 
+/* b200ms_rerank_device with one candidate list PER QUERY (the two-stage search of a query batch: every query reranks its own
+ * first-stage candidates, fast_multivector_store.py:526-557): cand_ids_dev = device [n_q, n_cand] page ids (-1 = unused slot).
+ * One launch per 128-token query tile scores that tile's queries against their own lists only; outputs as above. */
+int b200ms_rerank_batch_device(b200ms_t* h, const void* q_dev, int src_dtype, const int32_t* q_lens, int n_q,
+                               const int64_t* cand_ids_dev, int n_cand, int k, float i8_q_scale, float score_scale,
+                               float* top_scores_dev, int64_t* top_ids_dev, int32_t* top_counts_dev, void* stream);
+
+/* ---- multi-GPU: document shards, one NCCL all-gather of top-k lists (new relative to the reference) -------------
+ * One process per GPU; every rank owns a handle over its shard.  NCCL is bound at run time (dlopen libnccl.so.2, or the
+ * path in B200MS_NCCL_LIB); b200ms_comm_available() says whether that worked.
+ *   rank 0: b200ms_comm_unique_id(id) -> ship the 128 bytes to every rank by any means (file, socket, MPI, torch) ->
+ *   every rank: b200ms_comm_init(h, id, rank, world)      (collective; creates the handle's own communicator)
+ *   or b200ms_comm_adopt(h, ncclComm_t, rank, world) to use a communicator the host already has.
+ * Exchange layout of one rank's list ("xchg"): [n_q*k int64 global page ids][n_q*k float32 scores], b200ms_xchg_bytes(n_q,k)
+ * bytes, unused entries id -1 / score -inf -- b200ms_search_device can write it in place (top_ids_dev = xchg,
+ * top_scores_dev = xchg + n_q*k*8). */
+int b200ms_comm_available(void);
+int b200ms_comm_unique_id(uint8_t* id128);
+int b200ms_comm_init(b200ms_t* h, const uint8_t* id128, int rank, int world);
+int b200ms_comm_adopt(b200ms_t* h, void* nccl_comm, int rank, int world);
+int b200ms_comm_destroy(b200ms_t* h);
+int b200ms_comm_rank(const b200ms_t* h);
+int b200ms_comm_world(const b200ms_t* h);
+int64_t b200ms_xchg_bytes(int n_q, int k);
+/* ncclBroadcast of a device buffer from `root` (e.g. the query rows of a batch) on `stream`. */
+int b200ms_bcast_device(b200ms_t* h, void* buf, int64_t bytes, int root, void* stream);
+/* The one collective of the path: all-gather every rank's xchg block (nccl_comm NULL = the handle's communicator) and merge
+ * the world*k candidates per query -> identical top-k on every rank (score DESC, id ASC).  world * k <= 8192. */
+int b200ms_allgather_topk(b200ms_t* h, void* nccl_comm, const void* xchg_local_dev, int n_q, int k, float* top_scores_dev,
+                          int64_t* top_ids_dev, int32_t* top_counts_dev, void* stream);
+/* Pipelined sharded search.  _begin enqueues the local scan + top-k (global ids = id_base + local page) on `stream` and the
+ * all-gather + merge on the handle's communication stream behind an event, then returns a ticket (>= 0; negative = error);
+ * the caller's stream is NOT made to wait for the other ranks, so the next _begin may follow at once (two exchange slots: at
+ * most two searches in flight).  _end makes `stream` wait for that ticket's merged result in the output buffers given to
+ * _begin.  Masks as in b200ms_search_device_masked (n_masks = 0: unfiltered).  Works with world == 1 (no collective). */
+int64_t b200ms_sharded_search_begin(b200ms_t* h, const void* q_dev, int src_dtype, const int32_t* q_lens, int n_q, int k,
+                                    const uint32_t* allow_masks_dev, int n_masks, const int32_t* mask_index_dev,
+                                    float i8_q_scale, float score_scale, int64_t id_base, float* top_scores_dev,
+                                    int64_t* top_ids_dev, int32_t* top_counts_dev, void* stream);
+int b200ms_sharded_search_end(b200ms_t* h, int64_t ticket, void* stream);
+/* The same pipeline with HOST query rows (pinned or pageable float32) and host results: _host_begin copies the rows to the
+ * device on the handle's stream and returns at once; _host_end blocks until that ticket's merged top-k has been copied back
+ * and stores it in the caller's arrays.  Collect ticket t before beginning t+2. */
+int64_t b200ms_sharded_search_host_begin(b200ms_t* h, const float* q_host, const int32_t* q_lens, int n_q, int k,
+                                         const uint32_t* allow_masks_dev, int n_masks, const int32_t* mask_index_dev,
+                                         float i8_q_scale, float score_scale, int64_t id_base);
+int b200ms_sharded_search_host_end(b200ms_t* h, int64_t ticket, float* top_scores_host, int64_t* top_ids_host,
+                                   int32_t* top_counts_host);
+
 /* ---- fixed-dimensional encodings (MUVERA FDE): candidate generation in front of the scorer ---------------------------
  * Replaces the `fixed_dimensional_encoding` C++ extension (fast_multivector_store.py:325-331,447-449,521) and the
  * Turbopuffer ANN over its output (:526-532) with an exact encoder and an exhaustive cosine scan.
@@ -180,9 +233,22 @@ int b200ms_rerank_device(b200ms_t* h, const void* q_dev, int src_dtype, const in
  *   group_offsets = 0..n_q) to get the candidate list. */
 int b200ms_fde_configure(b200ms_t* h, int reps, int ksim, int proj_dim, float scale, const float* simhash,
                          const int32_t* ams_index, const float* ams_sign);
+/* configure + the upstream knobs the reference leaves at their defaults (fast_multivector_store.py:325-331 sets neither):
+ *   fill_empty_partitions != 0: an empty document partition takes the projection of the point whose SimHash sign bits are
+ *     nearest (Hamming distance, first minimum) instead of zeros;
+ *   final_dim > 0: a final count sketch of the whole encoding, out[j] = sum_{i: final_index[i]==j} final_sign[i] * v[i]
+ *     (final_index / final_sign: HOST arrays of reps*2^ksim*proj_dim entries; final_dim a multiple of 8) -- fde_dim becomes
+ *     final_dim.  The matrices are INPUTS: a caller that holds the upstream extension's matrices passes them here and gets
+ *     encodings interchangeable with vectors already stored by the reference. */
+int b200ms_fde_configure_ex(b200ms_t* h, int reps, int ksim, int proj_dim, float scale, const float* simhash,
+                            const int32_t* ams_index, const float* ams_sign, int fill_empty_partitions, int final_dim,
+                            const int32_t* final_index, const float* final_sign);
 int64_t b200ms_fde_dim(const b200ms_t* h);
 int b200ms_fde_encode(b200ms_t* h, const void* rows, int src_dtype, const int32_t* item_lens, int64_t n_items,
                       int is_document, float* out, void* stream);
+/* Document FDEs of pages [first_page, first_page + n_pages) of the attached BF16 corpus, computed from its packed rows
+ * (rebuilds the FDE matrix of a corpus loaded from a shard file; at most 65535 pages per call). */
+int b200ms_fde_encode_corpus(b200ms_t* h, int64_t first_page, int64_t n_pages, float* out, void* stream);
 int b200ms_fde_finalize(b200ms_t* h, const float* fde, int64_t n, void* out_rows, float* inv_norm, void* stream);
 int b200ms_fde_scan(b200ms_t* h, const void* fde_rows, const float* inv_norm, int64_t n_pages, const float* q_fde, int n_q,
                     float* scores, int64_t ld, void* stream);
@@ -200,11 +266,18 @@ int64_t b200ms_score_call_count(const b200ms_t* h);
 int b200ms_score_times_ms(b200ms_t* h, float* out_ms, int n);
 /* Tuning knobs (0 keeps the default): rows per work unit, CTAs to launch. */
 int b200ms_set_tuning(b200ms_t* h, int64_t unit_rows, int max_ctas);
-/* Named options: "a_in_tmem" (0 = query operand of tcgen05.mma from shared memory, 1 = from TMEM), "b1_tensor" (1 = score
- * 1-bit corpora on tcgen05 with in-kernel bit expansion, 0 = POPC kernel, 2 = auto by query-group count), "split4" (replicated-
- * query epilogue for single-group scans: 0 off (default), 1 = bf16 only, 2 = all dtypes), "epi_w4" (1 = four-epilogue-warpgroup
- * kernel for batches of >= 4 query tiles, default), "pair_cta" (CTA pairs with tcgen05 cta_group::2, M = N = 256:
- * 0 = off, 1 = passes of >= 3 query tiles, 2 = also exactly 2 tiles (default)), "unit_rows", "max_ctas".  Changing unit_rows needs a new b200ms_set_corpus to take effect. */
+/* Named options:
+ *   "pair_cta"        CTA pairs with tcgen05 cta_group::2, M = N = 256: 0 = off, 1 = passes of >= 3 query tiles, 2 = also
+ *                     exactly 2 tiles (default)
+ *   "b1_tensor"       1 = score 1-bit corpora on tcgen05 with in-kernel bit expansion, 0 = POPC kernel, 2 = auto by group count
+ *   "zero_pad_compat" N > 0: reproduce colpali_engine score_multi_vector's zero-padding quirk with batch size N (128 upstream,
+ *                     processing_colpali.py:350-362): a page shorter than the longest page of its batch scores
+ *                     sum_t max(max_r <q_t,d_r>, 0).  Rerank calls batch the candidates in first-stage order (exactly the
+ *                     reference, fast_multivector_store.py:553-555); full scans batch pages in page-id order.  0 = clean MaxSim
+ *                     (default).  Float and int8 corpora only -- SQL max_sim has no padding.
+ *   "zero_copy"       1 (default): host entry points move small calls (<= 256 query rows) through mapped pinned memory
+ *   "fde_gemm"        1 (default): FDE scan on tcgen05 when fde_dim % 64 == 0, 0 = SIMT scan
+ *   "unit_rows", "max_ctas"   work-unit size (needs a new b200ms_set_corpus) and launch width. */
 int b200ms_set_option(b200ms_t* h, const char* name, int64_t value);
 
 #ifdef __cplusplus

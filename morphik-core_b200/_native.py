@@ -13,9 +13,10 @@ from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_uint32
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libb200ms.so")
 
-F32, BF16, I8, B1, I32 = 0, 1, 2, 3, 4
-DTYPE_NAMES = {"f32": F32, "bf16": BF16, "int8": I8, "i8": I8, "binary": B1, "b1": B1, "1bit": B1}
-ROW_BYTES = {F32: 512, BF16: 256, I8: 128, B1: 16}
+F32, BF16, I8, B1, I32, F8 = 0, 1, 2, 3, 4, 5
+DTYPE_NAMES = {"f32": F32, "bf16": BF16, "int8": I8, "i8": I8, "binary": B1, "b1": B1, "1bit": B1, "fp8": F8, "f8": F8,
+               "e4m3": F8}
+ROW_BYTES = {F32: 512, BF16: 256, I8: 128, B1: 16, F8: 128}
 DIM = 128
 ROW_GROUP = 32
 MAX_K = 4096
@@ -70,10 +71,28 @@ def _load() -> ctypes.CDLL:
         "b200ms_set_tuning": (c_int, [vp, c_int64, c_int]),
         "b200ms_set_option": (c_int, [vp, c_char_p, c_int64]),
         "b200ms_rerank_device": (c_int, [vp, vp, c_int, i32p, c_int, vp, c_int, c_int, c_float, c_float, vp, vp, vp, vp]),
+        "b200ms_rerank_batch_device": (c_int, [vp, vp, c_int, i32p, c_int, vp, c_int, c_int, c_float, c_float, vp, vp, vp, vp]),
+        "b200ms_comm_available": (c_int, []),
+        "b200ms_comm_unique_id": (c_int, [vp]),
+        "b200ms_comm_init": (c_int, [vp, vp, c_int, c_int]),
+        "b200ms_comm_adopt": (c_int, [vp, vp, c_int, c_int]),
+        "b200ms_comm_destroy": (c_int, [vp]),
+        "b200ms_comm_rank": (c_int, [vp]),
+        "b200ms_comm_world": (c_int, [vp]),
+        "b200ms_xchg_bytes": (c_int64, [c_int, c_int]),
+        "b200ms_bcast_device": (c_int, [vp, vp, c_int64, c_int, vp]),
+        "b200ms_allgather_topk": (c_int, [vp, vp, vp, c_int, c_int, vp, vp, vp, vp]),
+        "b200ms_sharded_search_begin": (c_int64, [vp, vp, c_int, i32p, c_int, c_int, vp, c_int, vp, c_float, c_float, c_int64, vp,
+                                        vp, vp, vp]),
+        "b200ms_sharded_search_end": (c_int, [vp, c_int64, vp]),
+        "b200ms_sharded_search_host_begin": (c_int64, [vp, vp, i32p, c_int, c_int, vp, c_int, vp, c_float, c_float, c_int64]),
+        "b200ms_sharded_search_host_end": (c_int, [vp, c_int64, vp, vp, vp]),
+        "b200ms_fde_configure_ex": (c_int, [vp, c_int, c_int, c_int, c_float, vp, vp, vp, c_int, c_int, vp, vp]),
         "b200ms_fde_configure": (c_int, [vp, c_int, c_int, c_int, c_float, vp, vp, vp]),
         "b200ms_fde_dim": (c_int64, [vp]),
         "b200ms_fde_encode": (c_int, [vp, vp, c_int, i32p, c_int64, c_int, vp, vp]),
         "b200ms_fde_finalize": (c_int, [vp, vp, c_int64, vp, vp, vp]),
+        "b200ms_fde_encode_corpus": (c_int, [vp, c_int64, c_int64, vp, vp]),
         "b200ms_fde_scan": (c_int, [vp, vp, vp, c_int64, vp, c_int, vp, c_int64, vp]),
         "b200ms_score_call_count": (c_int64, [vp]),
         "b200ms_score_times_ms": (c_int, [vp, f32p, c_int]),
@@ -93,7 +112,11 @@ EXPORTED = [
     "b200ms_score", "b200ms_topk", "b200ms_merge_topk", "b200ms_search_host", "b200ms_search_host_masked", "b200ms_search_device", "b200ms_search_device_masked",
     "b200ms_launch_count", "b200ms_last_score_ms", "b200ms_set_tuning", "b200ms_score_call_count",
     "b200ms_score_times_ms", "b200ms_set_option", "b200ms_rerank_device", "b200ms_fde_configure", "b200ms_fde_dim",
-    "b200ms_fde_encode", "b200ms_fde_finalize", "b200ms_fde_scan", "b200ms_hamming_batch",
+    "b200ms_fde_encode", "b200ms_fde_finalize", "b200ms_fde_scan", "b200ms_hamming_batch", "b200ms_rerank_batch_device",
+    "b200ms_comm_available", "b200ms_comm_unique_id", "b200ms_comm_init", "b200ms_comm_adopt", "b200ms_comm_destroy",
+    "b200ms_comm_rank", "b200ms_comm_world", "b200ms_xchg_bytes", "b200ms_bcast_device", "b200ms_allgather_topk",
+    "b200ms_sharded_search_begin", "b200ms_sharded_search_end", "b200ms_sharded_search_host_begin",
+    "b200ms_sharded_search_host_end", "b200ms_fde_configure_ex", "b200ms_fde_encode_corpus",
 ]
 
 

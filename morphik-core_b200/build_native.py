@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIB_DIR, "libb200ms.so")
-SOURCES = ["api.cu", "maxsim_umma.cu", "maxsim_umma_pair.cu", "maxsim_b1.cu", "maxsim_b1_umma.cu", "pack.cu", "topk.cu", "fde.cu"]
+SOURCES = ["api.cu", "maxsim_umma.cu", "maxsim_umma_pair.cu", "maxsim_b1.cu", "maxsim_b1_umma.cu", "pack.cu", "topk.cu", "fde.cu", "comm.cu"]
 HEADERS = ["common.cuh", "ptx.cuh", "umma_tile.cuh", os.path.join("..", "..", "include", "b200ms.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -81,7 +81,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         print("\n".join(log))
     if failed:
         raise RuntimeError("nvcc failed; see output above")
-    link = [_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs
+    link = [_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs + ["-ldl"]
     subprocess.run(link, check=True)
     with open(STAMP, "w") as f:
         f.write(source_hash() + "\n")

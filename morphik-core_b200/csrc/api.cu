@@ -1,6 +1,7 @@
 // api.cu -- the extern "C" surface declared in include/b200ms.h: handle management, corpus attachment
 // (chunk table, work-unit plan, TMA descriptor), query packing and the fused search entry points.
 // Host-side C++ only orchestrates; all arithmetic on embeddings happens in the CUDA kernels.
+// (Multi-GPU entry points -- NCCL communicator, all-gather of top-k lists, pipelined sharded search -- live in comm.cu.)
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -45,6 +46,22 @@ int reserve(b200ms_t* h, DeviceBuf& b, size_t bytes) {
   return B200MS_OK;
 }
 
+int reserve_pinned(b200ms_t* h, PinnedBuf& b, size_t bytes) {
+  if (bytes <= b.cap) return B200MS_OK;
+  if (b.p) cudaFreeHost(b.p);
+  b.p = nullptr;
+  b.cap = 0;
+  const size_t want = ((bytes + bytes / 4) + 4095) & ~size_t(4095);
+  // cudaHostAllocMapped: with unified addressing the same pointer is valid in kernels (zero-copy reads / writes over PCIe)
+  if (cudaError_t e = cudaHostAlloc(&b.p, want, cudaHostAllocMapped | cudaHostAllocPortable); e != cudaSuccess) {
+    b.p = nullptr;
+    cudaGetLastError();
+    return set_error(h, B200MS_ENOMEM, "cudaHostAlloc of " + std::to_string(want) + " pinned bytes failed");
+  }
+  b.cap = want;
+  return B200MS_OK;
+}
+
 int upload(b200ms_t* h, DeviceBuf& b, const void* src, size_t bytes, cudaStream_t s) {
   if (int e = reserve(h, b, bytes ? bytes : 16)) return e;
   if (bytes == 0) return B200MS_OK;
@@ -55,30 +72,34 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
+// Resolved once per process, thread-safe (handles on different threads may attach corpora concurrently).
 static EncodeTiledFn encode_fn(b200ms_t* h) {
+  static std::once_flag once;
   static EncodeTiledFn fn = nullptr;
-  if (!fn) {
+  std::call_once(once, [] {
     void* p = nullptr;
     cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
-        q != cudaDriverEntryPointSuccess || !p) {
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess && p) {
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+    } else {
       cudaGetLastError();
-      set_error(h, B200MS_ECUDA, "cuTensorMapEncodeTiled not available from the driver");
-      return nullptr;
     }
-    fn = reinterpret_cast<EncodeTiledFn>(p);
-  }
+  });
+  if (!fn) set_error(h, B200MS_ECUDA, "cuTensorMapEncodeTiled not available from the driver");
   return fn;
 }
 
-// [n_rows, 128] row-major view; box = one 128-byte K panel x box_rows rows, 128-byte swizzle (what the UMMA
-// K-major SWIZZLE_128B descriptor expects).  Out-of-range rows read as zero.
-int make_tmap_rows(b200ms_t* h, CUtensorMap* out, const void* base, int dtype, int64_t n_rows, int box_rows) {
+// [n_rows, row_bytes] row-major view; box = one 128-byte K panel x box_rows rows, 128-byte swizzle (what the UMMA
+// K-major SWIZZLE_128B descriptor expects).  Out-of-range rows read as zero.  row_bytes is 256 for bf16 rows and 128 for
+// the one-byte dtypes by default; the FDE matrix passes its own (fde_dim * 2).
+int make_tmap_rows(b200ms_t* h, CUtensorMap* out, const void* base, int dtype, int64_t n_rows, int box_rows, int64_t row_bytes) {
   EncodeTiledFn fn = encode_fn(h);
   if (!fn) return B200MS_ECUDA;
   const bool bf16 = dtype == B200MS_BF16;
-  const cuuint64_t dims[2] = {cuuint64_t(kDim), cuuint64_t(n_rows > 0 ? n_rows : 1)};
-  const cuuint64_t strides[1] = {cuuint64_t(bf16 ? 256 : 128)};
+  if (row_bytes <= 0) row_bytes = bf16 ? 256 : 128;
+  const cuuint64_t dims[2] = {cuuint64_t(bf16 ? row_bytes / 2 : row_bytes), cuuint64_t(n_rows > 0 ? n_rows : 1)};
+  const cuuint64_t strides[1] = {cuuint64_t(row_bytes)};
   const cuuint32_t box[2] = {cuuint32_t(bf16 ? 64 : 128), cuuint32_t(box_rows)};
   const cuuint32_t estr[2] = {1, 1};
   const CUresult r = fn(out, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 2,
@@ -89,21 +110,57 @@ int make_tmap_rows(b200ms_t* h, CUtensorMap* out, const void* base, int dtype, i
   return B200MS_OK;
 }
 
-static bool corpus_dtype_ok(int d) { return d == B200MS_BF16 || d == B200MS_I8 || d == B200MS_B1; }
+static bool corpus_dtype_ok(int d) { return d == B200MS_BF16 || d == B200MS_I8 || d == B200MS_B1 || d == B200MS_F8; }
 static bool src_dtype_ok(int d) { return d == B200MS_F32 || d == B200MS_BF16; }
 
-struct DeviceGuard {
-  int prev = -1;
-  explicit DeviceGuard(int dev) {
-    cudaGetDevice(&prev);
-    if (prev != dev) cudaSetDevice(dev);
-  }
-  ~DeviceGuard() {
-    int cur = -1;
-    cudaGetDevice(&cur);
-    if (prev >= 0 && cur != prev) cudaSetDevice(prev);
-  }
+DeviceGuard::DeviceGuard(int dev) {
+  cudaGetDevice(&prev);
+  if (prev != dev) cudaSetDevice(dev);
+}
+DeviceGuard::~DeviceGuard() {
+  int cur = -1;
+  cudaGetDevice(&cur);
+  if (prev >= 0 && cur != prev) cudaSetDevice(prev);
+}
+
+// ---- per-call metadata: ONE block (host-built) -> one upload, or read in place when the block is mapped pinned memory
+struct SearchMeta {
+  std::vector<uint8_t> host;  // [ss int64 (n_q+1) | ds int64 (n_q+1) | goff int32 (n_q+1) | ntok int32 (groups_padded)]
+  size_t off_ss = 0, off_ds = 0, off_goff = 0, off_ntok = 0;
+  int64_t rows = 0, groups = 0, groups_padded = 0;
+  std::vector<int32_t> goff;
 };
+
+static void build_search_meta(const int32_t* q_lens, int n_q, SearchMeta* m) {
+  const int64_t groups = b200ms_query_groups(q_lens, n_q);
+  m->groups = groups;
+  m->groups_padded = (groups + 3) & ~int64_t(3);
+  const size_t n1 = size_t(n_q) + 1;
+  m->off_ss = 0;
+  m->off_ds = n1 * 8;
+  m->off_goff = 2 * n1 * 8;
+  m->off_ntok = m->off_goff + ((n1 * 4 + 15) & ~size_t(15));
+  m->host.assign(m->off_ntok + size_t(m->groups_padded > 0 ? m->groups_padded : 4) * 4, 0);
+  int64_t* ss = reinterpret_cast<int64_t*>(m->host.data() + m->off_ss);
+  int64_t* ds = reinterpret_cast<int64_t*>(m->host.data() + m->off_ds);
+  int32_t* goff = reinterpret_cast<int32_t*>(m->host.data() + m->off_goff);
+  int32_t* ntok = reinterpret_cast<int32_t*>(m->host.data() + m->off_ntok);
+  ss[0] = ds[0] = 0;
+  goff[0] = 0;
+  for (int i = 0; i < n_q; ++i) {
+    const int64_t len = q_lens[i] > 0 ? q_lens[i] : 0;
+    ss[i + 1] = ss[i] + len;
+    ds[i + 1] = ds[i] + b200ms_padded_len(len);
+    goff[i + 1] = int32_t(ds[i + 1] / kGroup);
+    int64_t left = len;
+    for (int g = goff[i]; g < goff[i + 1]; ++g) {
+      ntok[g] = int32_t(left > kGroup ? kGroup : left);
+      left -= ntok[g];
+    }
+  }
+  m->rows = ss[n_q];
+  m->goff.assign(goff, goff + n1);
+}
 
 }  // namespace bms
 
@@ -147,19 +204,20 @@ B200MS_API int b200ms_create(int device, b200ms_t** out) {
   b200ms_t* h = new b200ms_t();
   h->device = device;
   h->num_sms = prop.multiProcessorCount;
-  if (const char* e = getenv("B200MS_A_IN_TMEM")) h->a_in_tmem = atoi(e) != 0;
   if (const char* e = getenv("B200MS_B1_TENSOR")) h->b1_tensor = atoi(e);
-  if (const char* e = getenv("B200MS_SPLIT4")) h->split4 = atoi(e);
-  if (const char* e = getenv("B200MS_EPI_W4")) h->epi_w4 = atoi(e) != 0;
   if (const char* e = getenv("B200MS_PAIR_CTA")) h->pair_cta = atoi(e);
+  if (const char* e = getenv("B200MS_ZERO_COPY")) h->zero_copy = atoi(e);
   if (const char* e = getenv("B200MS_UNIT_ROWS")) { if (atoll(e) > 0) h->unit_rows = atoll(e); }
   if (int e = check_cuda(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking), "cudaStreamCreate")) {
     delete h;
     return e;
   }
   for (int i = 0; i < b200ms_t::kEvRing; ++i) {
-    cudaEventCreate(&h->ev0[i]);
-    cudaEventCreate(&h->ev1[i]);
+    if (cudaEventCreate(&h->ev0[i]) != cudaSuccess || cudaEventCreate(&h->ev1[i]) != cudaSuccess) {
+      const int e = check_cuda(nullptr, cudaGetLastError(), "create: cudaEventCreate");
+      b200ms_destroy(h);
+      return e ? e : B200MS_ECUDA;
+    }
   }
   *out = h;
   return B200MS_OK;
@@ -169,11 +227,15 @@ B200MS_API int b200ms_destroy(b200ms_t* h) {
   if (!h) return B200MS_OK;
   DeviceGuard g(h->device);
   cudaDeviceSynchronize();
-  DeviceBuf* bufs[] = {&h->chunk_page, &h->unit_start, &h->page_start, &h->meta_a, &h->meta_b, &h->meta_c, &h->q_raw,
-                       &h->q_packed, &h->scores, &h->mask, &h->out_s, &h->out_i, &h->out_c, &h->cand_start, &h->cand_end,
-                       &h->cand_mask, &h->topk_keys, &h->topk_ids, &h->b1_q_i8, &h->b1_tok_const, &h->fde_simhash, &h->fde_ams_index, &h->fde_ams_sign, &h->fde_tmp};
+  comm_teardown(h);
+  DeviceBuf* bufs[] = {&h->chunk_page, &h->unit_start, &h->page_start, &h->page_len, &h->clamp_pages, &h->clamp_slots,
+                       &h->meta, &h->meta_b, &h->q_raw, &h->q_packed, &h->scores, &h->mask, &h->mask_index, &h->out_all,
+                       &h->cand_pad, &h->cand_start, &h->cand_end, &h->cand_mask, &h->topk_keys, &h->topk_ids, &h->b1_q_i8, &h->b1_tok_const,
+                       &h->fde_simhash, &h->fde_ams_index, &h->fde_ams_sign, &h->fde_tmp, &h->fde_q_bf16, &h->fde_final_index,
+                       &h->fde_final_sign};
   for (DeviceBuf* b : bufs)
     if (b->p) cudaFree(b->p);
+  if (h->stage.p) cudaFreeHost(h->stage.p);
   for (int i = 0; i < b200ms_t::kEvRing; ++i) {
     if (h->ev0[i]) cudaEventDestroy(h->ev0[i]);
     if (h->ev1[i]) cudaEventDestroy(h->ev1[i]);
@@ -196,6 +258,7 @@ B200MS_API int64_t b200ms_row_bytes(int dtype) {
     case B200MS_F32: return 512;
     case B200MS_BF16: return 256;
     case B200MS_I8: return 128;
+    case B200MS_F8: return 128;
     case B200MS_B1: return 16;
     default: return 0;
   }
@@ -219,16 +282,16 @@ B200MS_API int b200ms_set_tuning(b200ms_t* h, int64_t unit_rows, int max_ctas) {
 B200MS_API int b200ms_set_option(b200ms_t* h, const char* name, int64_t value) {
   if (!h || !name) return B200MS_EINVAL;
   const std::string n(name);
-  if (n == "a_in_tmem") {
-    h->a_in_tmem = value != 0;
-  } else if (n == "epi_w4") {
-    h->epi_w4 = value != 0;
-  } else if (n == "pair_cta") {
+  if (n == "pair_cta" && value >= 0 && value <= 2) {
     h->pair_cta = int(value);
-  } else if (n == "split4" && value >= 0 && value <= 2) {
-    h->split4 = int(value);
   } else if (n == "b1_tensor" && value >= 0 && value <= 2) {
     h->b1_tensor = int(value);
+  } else if (n == "zero_pad_compat" && value >= 0 && value <= (int64_t(1) << 30)) {
+    h->zero_pad_batch = int(value);
+  } else if (n == "zero_copy" && value >= 0 && value <= 1) {
+    h->zero_copy = int(value);
+  } else if (n == "fde_gemm" && value >= 0 && value <= 1) {
+    h->fde_gemm = int(value);
   } else if (n == "unit_rows" && value > 0) {
     h->unit_rows = value;
   } else if (n == "max_ctas" && value >= 0) {
@@ -246,7 +309,10 @@ B200MS_API int64_t b200ms_corpus_rows(const b200ms_t* h) { return h ? h->corpus.
 static int pack_items(b200ms_t* h, const void* src, int src_dtype, const int32_t* lens, int64_t n, bool queries,
                       void* dst, int dst_dtype, int64_t dst_rows_total, float i8_scale, cudaStream_t s,
                       std::vector<int64_t>* dst_start_out) {
-  std::vector<int64_t> ss(size_t(n) + 1), ds(size_t(n) + 1);
+  // one metadata block [ss | ds], one upload
+  std::vector<int64_t> sd(2 * (size_t(n) + 1));
+  int64_t* ss = sd.data();
+  int64_t* ds = sd.data() + n + 1;
   ss[0] = ds[0] = 0;
   for (int64_t i = 0; i < n; ++i) {
     const int64_t len = lens[i] > 0 ? lens[i] : 0;
@@ -254,14 +320,12 @@ static int pack_items(b200ms_t* h, const void* src, int src_dtype, const int32_t
     ds[i + 1] = ds[i] + b200ms_padded_len(len);
   }
   const int64_t dst_rows = dst_rows_total >= 0 ? dst_rows_total : ds[n];
-  if (int e = upload(h, h->meta_a, ss.data(), ss.size() * 8, s)) return e;
-  if (int e = upload(h, h->meta_b, ds.data(), ds.size() * 8, s)) return e;
-  if (int e = launch_pack_rows(h, src, src_dtype, static_cast<const int64_t*>(h->meta_a.p),
-                               static_cast<const int64_t*>(h->meta_b.p), n, dst_rows, queries ? 1 : 0, dst, dst_dtype,
-                               i8_scale, s))
+  if (int e = upload(h, h->meta_b, sd.data(), sd.size() * 8, s)) return e;
+  const int64_t* dev = static_cast<const int64_t*>(h->meta_b.p);
+  if (int e = launch_pack_rows(h, src, src_dtype, dev, dev + n + 1, n, dst_rows, queries ? 1 : 0, dst, dst_dtype, i8_scale, s))
     return e;
-  // ss/ds are pageable host memory: cudaMemcpyAsync staged them before returning, so they may die here
-  if (dst_start_out) *dst_start_out = std::move(ds);
+  // sd is pageable host memory: cudaMemcpyAsync staged it before returning, so it may die here
+  if (dst_start_out) dst_start_out->assign(ds, ds + n + 1);
   return B200MS_OK;
 }
 
@@ -273,8 +337,8 @@ B200MS_API int b200ms_sign_pack(b200ms_t* h, const void* x, int src_dtype, int64
   DeviceGuard g(h->device);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int64_t st[2] = {0, rows};
-  if (int e = upload(h, h->meta_a, st, sizeof(st), s)) return e;
-  const int64_t* d = static_cast<const int64_t*>(h->meta_a.p);
+  if (int e = upload(h, h->meta_b, st, sizeof(st), s)) return e;
+  const int64_t* d = static_cast<const int64_t*>(h->meta_b.p);
   return launch_pack_rows(h, x, src_dtype, d, d, 1, rows, 0, out, B200MS_B1, 1.f, s);
 }
 
@@ -364,6 +428,8 @@ B200MS_API int b200ms_set_corpus(b200ms_t* h, const void* rows, int dtype, const
   c.n_units = int(us.size()) - 1;
   if (int e = upload(h, h->page_start, ps.data(), ps.size() * 8, s)) return e;
   if (int e = upload(h, h->unit_start, us.data(), us.size() * 4, s)) return e;
+  if (int e = upload(h, h->page_len, page_lens, size_t(n_pages) * 4, s)) return e;
+  h->page_len_host.assign(page_lens, page_lens + n_pages);
   if (int e = reserve(h, h->chunk_page, size_t(c.n_chunks > 0 ? c.n_chunks : 1) * 4)) return e;
   if (int e = launch_chunk_page(h, static_cast<const int64_t*>(h->page_start.p), n_pages,
                                 static_cast<int32_t*>(h->chunk_page.p), s))
@@ -377,69 +443,136 @@ B200MS_API int b200ms_set_corpus(b200ms_t* h, const void* rows, int dtype, const
   return B200MS_OK;
 }
 
+// zero_pad_compat, full scan: pages are "batched" in page-id order, zero_pad_batch at a time (score_multi_vector's
+// batch_size, 128 upstream); a page shorter than the longest of its batch gets its per-token maxima clamped at 0.
+// Built on the host once per (corpus, batch size) and cached on the device.
+static int ensure_clamp_pages(b200ms_t* h, cudaStream_t s, const uint32_t** out) {
+  *out = nullptr;
+  if (h->zero_pad_batch <= 0 || h->corpus.dtype == B200MS_B1) return B200MS_OK;  // SQL max_sim has no padding quirk
+  Corpus& c = h->corpus;
+  const int64_t n = c.n_pages;
+  if (c.clamp_batch != h->zero_pad_batch) {
+    std::vector<uint32_t> bits(size_t((n + 31) / 32) + 1, 0u);
+    const int64_t B = h->zero_pad_batch;
+    for (int64_t b0 = 0; b0 < n; b0 += B) {
+      const int64_t b1 = b0 + B < n ? b0 + B : n;
+      int32_t mx = 0;
+      for (int64_t p = b0; p < b1; ++p) mx = h->page_len_host[p] > mx ? h->page_len_host[p] : mx;
+      for (int64_t p = b0; p < b1; ++p)
+        if (h->page_len_host[p] < mx) bits[size_t(p >> 5)] |= 1u << (p & 31);
+    }
+    if (int e = upload(h, h->clamp_pages, bits.data(), bits.size() * 4, s)) return e;
+    c.clamp_batch = h->zero_pad_batch;
+  }
+  *out = static_cast<const uint32_t*>(h->clamp_pages.p);
+  return B200MS_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ hot path
-// cand_ids == NULL: scan the whole corpus, scores indexed by page id.  Otherwise: score only the n_cand candidate pages
-// (device array of page ids, -1 = unused slot), scores indexed by candidate slot.
-static int score_impl(b200ms_t* h, const void* q_packed, int n_groups, const int32_t* q_lens,
-                      const int32_t* group_offsets, int n_q, void* group_scores, int64_t ld, const int64_t* cand_ids,
-                      int n_cand, cudaStream_t s) {
+// Candidate description for score_impl / search_impl.
+//   ids == NULL           : scan the whole corpus, scores indexed by page id.
+//   ids, per_query == 0   : ONE list of n_cand page ids (-1 = unused slot) scored by every query, scores indexed by slot.
+//   ids, per_query == 1   : one list PER QUERY, ids = [n_q, stride] with stride = roundup(n_cand, 32); query q owns slots
+//                           [q*stride, q*stride + n_cand) and only its own groups are scored against them.
+struct CandSpec {
+  const int64_t* ids = nullptr;
+  int n_cand = 0;
+  int per_query = 0;
+  int64_t stride = 0;
+  int64_t n_slots(int n_q) const { return per_query ? stride * n_q : n_cand; }
+};
+
+static int score_impl(b200ms_t* h, const void* q_packed, int n_groups, const int32_t* goff, int n_q, const int32_t* ntok_dev,
+                      void* group_scores, int64_t ld, const CandSpec& cs, cudaStream_t s) {
   const Corpus& c = h->corpus;
   if (c.dtype < 0) return set_error(h, B200MS_ESTATE, "score: no corpus attached (call b200ms_set_corpus first)");
-  const int64_t n_items = cand_ids ? n_cand : c.n_pages;
-  if (n_groups < 0 || ld < n_items || n_cand < 0 || (n_groups > 0 && (!q_packed || !group_scores)))
+  const int64_t n_items = cs.ids ? cs.n_slots(n_q) : c.n_pages;
+  if (n_groups < 0 || ld < n_items || cs.n_cand < 0 || (n_groups > 0 && (!q_packed || !group_scores)))
     return set_error(h, B200MS_EINVAL, "score: bad arguments");
   if (n_groups == 0 || n_items == 0 || c.n_pages == 0) return B200MS_OK;
   const int slot = int(h->ev_count % b200ms_t::kEvRing);
   const int n_groups_padded = (n_groups + 3) & ~3;
   if (c.dtype == B200MS_B1) {
-    if (!q_lens || !group_offsets || n_q <= 0) return set_error(h, B200MS_EINVAL, "score: B1 needs q_lens and group_offsets");
-    std::vector<int32_t> ntok(size_t(n_groups_padded), 0);
-    for (int q = 0; q < n_q; ++q) {
-      int left = q_lens[q];
-      for (int g = group_offsets[q]; g < group_offsets[q + 1] && g < n_groups; ++g) {
-        ntok[g] = left > kGroup ? kGroup : left;
-        left -= ntok[g];
-      }
-    }
-    if (int e = upload(h, h->meta_c, ntok.data(), ntok.size() * 4, s)) return e;
+    if (!goff || !ntok_dev || n_q <= 0) return set_error(h, B200MS_EINVAL, "score: B1 needs the per-group token counts");
     // b1_tensor: 0 = POPC kernel, 1 = tcgen05 kernel, 2 (default) = measured crossover: one 32-token group is faster on the
     // POPC pipe (1.59 vs 2.49 ms / 65536 pages), two or more groups on the tensor cores (a 128-token tile costs the same
     // as one token there).  Rerank of a candidate list stays on the POPC kernel.
-    const bool tensor_path = !cand_ids && (h->b1_tensor == 1 || (h->b1_tensor == 2 && n_groups >= 2));
-    if (tensor_path && c.has_empty)
+    const bool tensor_path = !cs.ids && (h->b1_tensor == 1 || (h->b1_tensor == 2 && n_groups >= 2));
+    if ((tensor_path && c.has_empty) || cs.per_query)
       if (int e = check_cuda(h, cudaMemsetAsync(group_scores, 0, size_t(n_groups_padded) * size_t(ld) * 4, s), "score: memset")) return e;
-    cudaEventRecord(h->ev0[slot], s);
+    if (int e = check_cuda(h, cudaEventRecord(h->ev0[slot], s), "score: event record")) return e;
     if (tensor_path) {
-      if (int e = launch_score_b1_umma(h, q_packed, static_cast<const int32_t*>(h->meta_c.p), n_groups, group_scores, ld, s)) return e;
+      if (int e = launch_score_b1_umma(h, q_packed, ntok_dev, n_groups, group_scores, ld, s)) return e;
+    } else if (cs.per_query) {
+      for (int q = 0; q < n_q; ++q) {
+        if (goff[q + 1] <= goff[q]) continue;
+        if (int e = launch_score_b1(h, cs.ids + int64_t(q) * cs.stride, cs.n_cand, q_packed, n_groups, ntok_dev,
+                                    static_cast<int32_t*>(group_scores) + int64_t(q) * cs.stride, ld, s, goff[q], goff[q + 1]))
+          return e;
+      }
     } else {
-      if (int e = launch_score_b1(h, cand_ids, n_cand, q_packed, n_groups, static_cast<const int32_t*>(h->meta_c.p),
-                                  group_scores, ld, s))
-        return e;
+      if (int e = launch_score_b1(h, cs.ids, cs.n_cand, q_packed, n_groups, ntok_dev, group_scores, ld, s, 0, n_groups)) return e;
     }
-    cudaEventRecord(h->ev1[slot], s);
+    if (int e = check_cuda(h, cudaEventRecord(h->ev1[slot], s), "score: event record")) return e;
     h->ev_count++;
-    // ntok is pageable host memory: the async upload staged it before returning, nothing else to wait for
     return B200MS_OK;
   }
   // pages with zero rows (and unused candidate slots) are never touched by the tile kernel: they score 0
-  if (c.has_empty || cand_ids) {
+  if (c.has_empty || cs.ids) {
     if (int e = check_cuda(h, cudaMemsetAsync(group_scores, 0, size_t(n_groups_padded) * size_t(ld) * 4, s), "score: memset")) return e;
   }
   UnitPlan plan;
-  if (cand_ids) {
-    if (int e = reserve(h, h->cand_start, size_t(n_cand) * 4)) return e;
-    if (int e = reserve(h, h->cand_end, size_t(n_cand) * 4)) return e;
-    if (int e = launch_cand_units(h, cand_ids, n_cand, static_cast<int32_t*>(h->cand_start.p),
+  if (cs.ids) {
+    const int n_slots = int(cs.n_slots(n_q));
+    if (int e = reserve(h, h->cand_start, size_t(n_slots) * 4)) return e;
+    if (int e = reserve(h, h->cand_end, size_t(n_slots) * 4)) return e;
+    if (int e = launch_cand_units(h, cs.ids, n_slots, static_cast<int32_t*>(h->cand_start.p),
                                   static_cast<int32_t*>(h->cand_end.p), nullptr, s))
       return e;
     plan.start = static_cast<const int32_t*>(h->cand_start.p);
     plan.end = static_cast<const int32_t*>(h->cand_end.p);
-    plan.n_units = n_cand;
+    plan.n_units = n_slots;
     plan.slot_mode = 1;
+    if (h->zero_pad_batch > 0) {  // the reference's quirk, exactly: batches of zero_pad_batch candidates in first-stage order
+      if (int e = reserve(h, h->clamp_slots, size_t((n_slots + 31) / 32 + 1) * 4)) return e;
+      const int lists = cs.per_query ? n_q : 1;
+      const int64_t stride = cs.per_query ? cs.stride : 0;
+      if (int e = launch_clamp_slots(h, cs.ids, cs.n_cand, lists, stride, h->zero_pad_batch,
+                                     static_cast<uint32_t*>(h->clamp_slots.p), s))
+        return e;
+      plan.clamp_bits = static_cast<const uint32_t*>(h->clamp_slots.p);
+    }
+  } else {  // full scan: unit u = [unit_start[u], unit_start[u+1])
+    plan.start = static_cast<const int32_t*>(h->unit_start.p);
+    plan.end = plan.start + 1;
+    plan.n_units = c.n_units;
+    plan.slot_mode = 0;
+    if (int e = ensure_clamp_pages(h, s, &plan.clamp_bits)) return e;
   }
-  cudaEventRecord(h->ev0[slot], s);
-  if (int e = launch_score_umma(h, cand_ids ? &plan : nullptr, q_packed, n_groups, group_scores, ld, s)) return e;
-  cudaEventRecord(h->ev1[slot], s);
+  if (int e = check_cuda(h, cudaEventRecord(h->ev0[slot], s), "score: event record")) return e;
+  if (cs.ids && cs.per_query) {
+    // one launch per 128-token query tile: the tile's queries against THEIR candidate lists only (a contiguous slot range)
+    const int n_mtiles = n_groups_padded / 4;
+    int q_lo = 0;
+    for (int m = 0; m < n_mtiles; ++m) {
+      const int g0 = 4 * m, g1 = 4 * m + 4;
+      while (q_lo < n_q && goff[q_lo + 1] <= g0) ++q_lo;  // first query with a group in this tile
+      int q_hi = q_lo;
+      while (q_hi < n_q && goff[q_hi] < g1) ++q_hi;        // one past the last
+      if (q_hi <= q_lo) continue;
+      UnitPlan sub = plan;
+      const int64_t s0 = int64_t(q_lo) * cs.stride;
+      sub.start += s0;
+      sub.end += s0;
+      sub.n_units = int(int64_t(q_hi - q_lo) * cs.stride);
+      if (sub.clamp_bits) sub.clamp_bits += s0 / 32;
+      void* sc = static_cast<uint8_t*>(group_scores) + size_t(s0) * 4;
+      if (int e = launch_score_umma(h, &sub, q_packed, n_groups, sc, ld, s, m, m + 1)) return e;
+    }
+  } else {
+    if (int e = launch_score_umma(h, &plan, q_packed, n_groups, group_scores, ld, s)) return e;
+  }
+  if (int e = check_cuda(h, cudaEventRecord(h->ev1[slot], s), "score: event record")) return e;
   h->ev_count++;
   return B200MS_OK;
 }
@@ -448,7 +581,23 @@ B200MS_API int b200ms_score(b200ms_t* h, const void* q_packed, int n_groups, con
                             const int32_t* group_offsets, int n_q, void* group_scores, int64_t ld, void* stream) {
   if (!h) return B200MS_EINVAL;
   DeviceGuard g(h->device);
-  return score_impl(h, q_packed, n_groups, q_lens, group_offsets, n_q, group_scores, ld, nullptr, 0, static_cast<cudaStream_t>(stream));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int32_t* ntok_dev = nullptr;
+  if (h->corpus.dtype == B200MS_B1) {
+    if (!q_lens || !group_offsets || n_q <= 0) return set_error(h, B200MS_EINVAL, "score: B1 needs q_lens and group_offsets");
+    const int n_groups_padded = (n_groups + 3) & ~3;
+    std::vector<int32_t> ntok(size_t(n_groups_padded > 0 ? n_groups_padded : 4), 0);
+    for (int q = 0; q < n_q; ++q) {
+      int left = q_lens[q];
+      for (int gi = group_offsets[q]; gi < group_offsets[q + 1] && gi < n_groups; ++gi) {
+        ntok[gi] = left > kGroup ? kGroup : left;
+        left -= ntok[gi];
+      }
+    }
+    if (int e = upload(h, h->meta, ntok.data(), ntok.size() * 4, s)) return e;
+    ntok_dev = static_cast<const int32_t*>(h->meta.p);
+  }
+  return score_impl(h, q_packed, n_groups, group_offsets, n_q, ntok_dev, group_scores, ld, CandSpec{}, s);
 }
 
 static int score_time_of(b200ms_t* h, int64_t idx, float* ms) {
@@ -489,8 +638,8 @@ B200MS_API int b200ms_topk(b200ms_t* h, const void* group_scores, int score_dtyp
   if (n_q == 0) return B200MS_OK;
   DeviceGuard g(h->device);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (int e = upload(h, h->meta_a, group_offsets, size_t(n_q + 1) * 4, s)) return e;
-  return launch_topk(h, group_scores, score_dtype, n_pages, ld, static_cast<const int32_t*>(h->meta_a.p), n_q, allow_mask,
+  if (int e = upload(h, h->meta, group_offsets, size_t(n_q + 1) * 4, s)) return e;
+  return launch_topk(h, group_scores, score_dtype, n_pages, ld, static_cast<const int32_t*>(h->meta.p), n_q, allow_mask,
                      k, scale, id_base, nullptr, top_scores, top_ids, top_counts, s);
 }
 
@@ -505,40 +654,83 @@ B200MS_API int b200ms_merge_topk(b200ms_t* h, const float* cand_scores, const in
                            static_cast<cudaStream_t>(stream));
 }
 
-static int search_impl(b200ms_t* h, const void* q_dev, int src_dtype, const int32_t* q_lens, int n_q, int k,
-                       const uint32_t* allow_dev, float i8_q_scale, float score_scale, int64_t id_base, float* ts,
-                       int64_t* ti, int32_t* tc, cudaStream_t s, const int64_t* cand_ids = nullptr, int n_cand = 0,
-                       const int32_t* mask_index_dev = nullptr, int64_t mask_stride = 0) {
+namespace bms {
+
+// The search step shared by every entry point: pack queries -> score -> top-k, all enqueued on `s`.
+//   q_src           rows [sum q_lens,128] F32|BF16, device memory or (zero-copy path) mapped pinned host memory
+//   meta_in_place   != NULL: the SearchMeta block already sits in device-readable memory at this address (mapped pinned
+//                   staging) -- no upload; else the block is uploaded with ONE cudaMemcpyAsync
+int search_core(b200ms_t* h, const void* q_src, int src_dtype, const int32_t* q_lens, int n_q, int k,
+                const uint32_t* allow_dev, float i8_q_scale, float score_scale, int64_t id_base, float* ts, int64_t* ti,
+                int32_t* tc, cudaStream_t s, const SearchCand* cand, const int32_t* mask_index_dev, int64_t mask_stride,
+                const void* meta_in_place, const void* meta_host_block) {
   const Corpus& c = h->corpus;
   if (c.dtype < 0) return set_error(h, B200MS_ESTATE, "search: no corpus attached (call b200ms_set_corpus first)");
-  if (n_q < 1 || !q_lens || !q_dev || k < 1 || k > B200MS_MAX_K || !ts || !ti || !tc)
+  if (n_q < 1 || !q_lens || !q_src || k < 1 || k > B200MS_MAX_K || !ts || !ti || !tc)
     return set_error(h, B200MS_EINVAL, "search: bad arguments (n_q >= 1, 1 <= k <= 4096)");
-  const int64_t groups = b200ms_query_groups(q_lens, n_q);
-  const int64_t groups_padded = (groups + 3) & ~int64_t(3);
-  const int64_t n_items = cand_ids ? n_cand : c.n_pages;
-  const int64_t ld = (n_items + 31) & ~int64_t(31);
-  if (int e = reserve(h, h->q_packed, size_t(groups_padded > 0 ? groups_padded : 4) * kGroup * size_t(b200ms_row_bytes(c.dtype)))) return e;
-  if (int e = reserve(h, h->scores, size_t(groups_padded > 0 ? groups_padded : 4) * size_t(ld > 0 ? ld : 32) * 4)) return e;
-  std::vector<int32_t> goff(size_t(n_q) + 1);
-  int ng = 0;
-  if (int e = b200ms_pack_queries(h, q_dev, src_dtype, q_lens, n_q, h->q_packed.p, c.dtype, i8_q_scale, goff.data(), &ng, s)) return e;
-  if (int e = score_impl(h, h->q_packed.p, ng, q_lens, goff.data(), n_q, h->scores.p, ld, cand_ids, n_cand, s)) return e;
+  SearchMeta local;
+  const SearchMeta* m = static_cast<const SearchMeta*>(meta_host_block);
+  if (!m) {
+    build_search_meta(q_lens, n_q, &local);
+    m = &local;
+  }
+  CandSpec cs;
+  if (cand && cand->ids) {
+    cs.ids = cand->ids;
+    cs.n_cand = cand->n_cand;
+    cs.per_query = cand->per_query;
+    cs.stride = cand->per_query ? ((int64_t(cand->n_cand) + 31) & ~int64_t(31)) : 0;
+    if (cs.per_query && cs.stride != cs.n_cand) {  // caller's lists are [n_q, n_cand]: give every list a 32-slot-aligned stride
+      if (int e = reserve(h, h->cand_pad, size_t(cs.stride) * size_t(n_q) * 8)) return e;
+      if (int e = launch_pad_cands(h, cand->ids, cs.n_cand, n_q, cs.stride, static_cast<int64_t*>(h->cand_pad.p), s)) return e;
+      cs.ids = static_cast<const int64_t*>(h->cand_pad.p);
+    }
+  }
+  const int64_t gp = m->groups_padded > 0 ? m->groups_padded : 4;
+  const int64_t n_items = cs.ids ? cs.n_slots(n_q) : c.n_pages;
+  const int64_t ld = ((n_items + 31) & ~int64_t(31)) > 0 ? ((n_items + 31) & ~int64_t(31)) : 32;
+  if (int e = reserve(h, h->q_packed, size_t(gp) * kGroup * size_t(b200ms_row_bytes(c.dtype)))) return e;
+  if (int e = reserve(h, h->scores, size_t(gp) * size_t(ld) * 4)) return e;
+  const uint8_t* meta_dev = static_cast<const uint8_t*>(meta_in_place);
+  if (!meta_dev) {
+    if (int e = upload(h, h->meta, m->host.data(), m->host.size(), s)) return e;
+    meta_dev = static_cast<const uint8_t*>(h->meta.p);
+  }
+  const int64_t* ss_dev = reinterpret_cast<const int64_t*>(meta_dev + m->off_ss);
+  const int64_t* ds_dev = reinterpret_cast<const int64_t*>(meta_dev + m->off_ds);
+  const int32_t* goff_dev = reinterpret_cast<const int32_t*>(meta_dev + m->off_goff);
+  const int32_t* ntok_dev = reinterpret_cast<const int32_t*>(meta_dev + m->off_ntok);
+  if (m->groups_padded > 0)
+    if (int e = launch_pack_rows(h, q_src, src_dtype, ss_dev, ds_dev, n_q, m->groups_padded * kGroup, 1, h->q_packed.p, c.dtype,
+                                 i8_q_scale, s))
+      return e;
+  const int ng = int(m->groups);
+  if (int e = score_impl(h, h->q_packed.p, ng, m->goff.data(), n_q, ntok_dev, h->scores.p, ld, cs, s)) return e;
   if (ng == 0 || n_items == 0) {
     // nothing scored: every page (if any) has score 0 -- still a defined ranking
-    if (int e = check_cuda(h, cudaMemsetAsync(h->scores.p, 0, size_t(groups_padded > 0 ? groups_padded : 4) * size_t(ld > 0 ? ld : 32) * 4, s), "search: memset")) return e;
+    if (int e = check_cuda(h, cudaMemsetAsync(h->scores.p, 0, size_t(gp) * size_t(ld) * 4, s), "search: memset")) return e;
   }
-  const int sdt = c.dtype == B200MS_BF16 ? B200MS_F32 : B200MS_I32;
-  if (!cand_ids) {
-    if (int e = upload(h, h->meta_a, goff.data(), size_t(n_q + 1) * 4, s)) return e;
-    return launch_topk(h, h->scores.p, sdt, c.n_pages, ld, static_cast<const int32_t*>(h->meta_a.p), n_q, allow_dev, k,
-                       score_scale, id_base, nullptr, ts, ti, tc, s, mask_index_dev, mask_stride);
+  const int sdt = (c.dtype == B200MS_BF16 || c.dtype == B200MS_F8) ? B200MS_F32 : B200MS_I32;
+  if (!cs.ids) {
+    return launch_topk(h, h->scores.p, sdt, c.n_pages, ld, goff_dev, n_q, allow_dev, k, score_scale, id_base, nullptr, ts, ti,
+                       tc, s, mask_index_dev, mask_stride);
   }
   // candidate mode: rank the slots (ties -> lower slot = better first-stage rank), report the page ids; unused slots masked
-  if (int e = reserve(h, h->cand_mask, size_t((n_cand + 31) / 32) * 4)) return e;
-  if (int e = launch_cand_units(h, cand_ids, n_cand, nullptr, nullptr, static_cast<uint32_t*>(h->cand_mask.p), s)) return e;
-  if (int e = upload(h, h->meta_a, goff.data(), size_t(n_q + 1) * 4, s)) return e;
-  return launch_topk(h, h->scores.p, sdt, n_cand, ld, static_cast<const int32_t*>(h->meta_a.p), n_q,
-                     static_cast<const uint32_t*>(h->cand_mask.p), k, score_scale, 0, cand_ids, ts, ti, tc, s);
+  const int n_slots = int(cs.n_slots(n_q));
+  if (int e = reserve(h, h->cand_mask, size_t((n_slots + 31) / 32 + 1) * 4)) return e;
+  if (int e = launch_cand_units(h, cs.ids, n_slots, nullptr, nullptr, static_cast<uint32_t*>(h->cand_mask.p), s)) return e;
+  return launch_topk(h, h->scores.p, sdt, cs.n_cand, ld, goff_dev, n_q, static_cast<const uint32_t*>(h->cand_mask.p), k,
+                     score_scale, 0, cs.ids, ts, ti, tc, s, nullptr, 0, cs.per_query ? cs.stride : 0);
+}
+
+}  // namespace bms
+
+static int search_impl(b200ms_t* h, const void* q_dev, int src_dtype, const int32_t* q_lens, int n_q, int k,
+                       const uint32_t* allow_dev, float i8_q_scale, float score_scale, int64_t id_base, float* ts,
+                       int64_t* ti, int32_t* tc, cudaStream_t s, const SearchCand* cand = nullptr,
+                       const int32_t* mask_index_dev = nullptr, int64_t mask_stride = 0) {
+  return search_core(h, q_dev, src_dtype, q_lens, n_q, k, allow_dev, i8_q_scale, score_scale, id_base, ts, ti, tc, s, cand,
+                     mask_index_dev, mask_stride, nullptr, nullptr);
 }
 
 B200MS_API int b200ms_rerank_device(b200ms_t* h, const void* q_dev, int src_dtype, const int32_t* q_lens, int n_q,
@@ -548,8 +740,22 @@ B200MS_API int b200ms_rerank_device(b200ms_t* h, const void* q_dev, int src_dtyp
   if (!src_dtype_ok(src_dtype) || !cand_ids_dev || n_cand < 1)
     return set_error(h, B200MS_EINVAL, "rerank_device: bad arguments (F32/BF16 queries, n_cand >= 1)");
   DeviceGuard g(h->device);
+  SearchCand cand{cand_ids_dev, n_cand, 0};
   return search_impl(h, q_dev, src_dtype, q_lens, n_q, k, nullptr, i8_q_scale, score_scale, 0, top_scores_dev, top_ids_dev,
-                     top_counts_dev, static_cast<cudaStream_t>(stream), cand_ids_dev, n_cand);
+                     top_counts_dev, static_cast<cudaStream_t>(stream), &cand);
+}
+
+B200MS_API int b200ms_rerank_batch_device(b200ms_t* h, const void* q_dev, int src_dtype, const int32_t* q_lens, int n_q,
+                                          const int64_t* cand_ids_dev, int n_cand, int k, float i8_q_scale, float score_scale,
+                                          float* top_scores_dev, int64_t* top_ids_dev, int32_t* top_counts_dev, void* stream) {
+  if (!h) return B200MS_EINVAL;
+  if (!src_dtype_ok(src_dtype) || !cand_ids_dev || n_cand < 1 || n_q < 1 ||
+      ((int64_t(n_cand) + 31) & ~int64_t(31)) * n_q >= (int64_t(1) << 30))
+    return set_error(h, B200MS_EINVAL, "rerank_batch_device: bad arguments (F32/BF16 queries, n_cand >= 1, n_q*n_cand < 2^30)");
+  DeviceGuard g(h->device);
+  SearchCand cand{cand_ids_dev, n_cand, 1};
+  return search_impl(h, q_dev, src_dtype, q_lens, n_q, k, nullptr, i8_q_scale, score_scale, 0, top_scores_dev, top_ids_dev,
+                     top_counts_dev, static_cast<cudaStream_t>(stream), &cand);
 }
 
 B200MS_API int b200ms_search_device(b200ms_t* h, const void* q_dev, int src_dtype, const int32_t* q_lens, int n_q, int k,
@@ -573,10 +779,16 @@ B200MS_API int b200ms_search_device_masked(b200ms_t* h, const void* q_dev, int s
     return set_error(h, B200MS_EINVAL, "search_device_masked: n_masks > 0 needs the mask matrix and one index per query");
   DeviceGuard g(h->device);
   return search_impl(h, q_dev, src_dtype, q_lens, n_q, k, n_masks > 0 ? allow_masks_dev : nullptr, i8_q_scale, score_scale,
-                     id_base, top_scores_dev, top_ids_dev, top_counts_dev, static_cast<cudaStream_t>(stream), nullptr, 0,
+                     id_base, top_scores_dev, top_ids_dev, top_counts_dev, static_cast<cudaStream_t>(stream), nullptr,
                      n_masks > 0 ? mask_index_dev : nullptr, (h->corpus.n_pages + 31) / 32);
 }
 
+// Host entry point.  Two transports, same kernels:
+//   zero-copy (small calls, the interactive case: <= 256 query rows and <= 64 KB of results): the query rows and the
+//     per-call metadata are written into ONE handle-owned mapped pinned block that the pack / top-k kernels read in
+//     place, and the top-k kernel writes its results straight into the same block -- no copy-engine operation and no
+//     metadata upload on the critical path (round 1 spent ~12 driver calls, 4 of them pageable uploads, around a 15 us scan).
+//   copy engine (batches): one H2D of the rows, one upload of the metadata block, one fused D2H of [scores|ids|counts].
 static int search_host_impl(b200ms_t* h, const float* q_host, const int32_t* q_lens, int n_q, int k,
                             const uint32_t* masks_host, int n_masks, const int32_t* mask_index_host, float i8_q_scale,
                             float score_scale, int64_t id_base, float* top_scores_host, int64_t* top_ids_host,
@@ -585,36 +797,56 @@ static int search_host_impl(b200ms_t* h, const float* q_host, const int32_t* q_l
     return set_error(h, B200MS_EINVAL, "search_host: bad arguments (n_q >= 1, 1 <= k <= 4096)");
   DeviceGuard g(h->device);
   cudaStream_t s = h->stream;
-  int64_t rows = 0;
-  for (int i = 0; i < n_q; ++i) rows += q_lens[i] > 0 ? q_lens[i] : 0;
-  if (int e = reserve(h, h->q_raw, size_t(rows > 0 ? rows : 1) * kDim * 4)) return e;
-  if (int e = reserve(h, h->out_s, size_t(n_q) * k * 4)) return e;
-  if (int e = reserve(h, h->out_i, size_t(n_q) * k * 8)) return e;
-  if (int e = reserve(h, h->out_c, size_t(n_q) * 4)) return e;
-  if (rows > 0)
-    if (int e = check_cuda(h, cudaMemcpyAsync(h->q_raw.p, q_host, size_t(rows) * kDim * 4, cudaMemcpyHostToDevice, s), "search_host: H2D queries")) return e;
+  SearchMeta m;
+  build_search_meta(q_lens, n_q, &m);
+  const size_t q_bytes = size_t(m.rows > 0 ? m.rows : 0) * kDim * 4;
+  const size_t nk = size_t(n_q) * size_t(k);
+  const size_t out_ids_off = 0, out_scores_off = nk * 8, out_counts_off = nk * 12;
+  const size_t out_bytes = (nk * 12 + size_t(n_q) * 4 + 15) & ~size_t(15);
   const uint32_t* allow_dev = nullptr;
   const int32_t* index_dev = nullptr;
   const int64_t words = (h->corpus.n_pages + 31) / 32;
   if (masks_host && n_masks > 0 && h->corpus.n_pages > 0) {
-    if (int e = upload(h, h->mask, masks_host, size_t(n_masks) * size_t(words) * 4, s)) return e;
-    allow_dev = static_cast<const uint32_t*>(h->mask.p);
-    if (mask_index_host) {
+    if (mask_index_host)
       for (int i = 0; i < n_q; ++i)
         if (mask_index_host[i] < -1 || mask_index_host[i] >= n_masks)
           return set_error(h, B200MS_EINVAL, "search_host_masked: mask_index out of range");
+    if (int e = upload(h, h->mask, masks_host, size_t(n_masks) * size_t(words) * 4, s)) return e;
+    allow_dev = static_cast<const uint32_t*>(h->mask.p);
+    if (mask_index_host) {
       if (int e = upload(h, h->mask_index, mask_index_host, size_t(n_q) * 4, s)) return e;
       index_dev = static_cast<const int32_t*>(h->mask_index.p);
     }
   }
-  if (int e = search_impl(h, h->q_raw.p, B200MS_F32, q_lens, n_q, k, allow_dev, i8_q_scale, score_scale, id_base,
-                          static_cast<float*>(h->out_s.p), static_cast<int64_t*>(h->out_i.p),
-                          static_cast<int32_t*>(h->out_c.p), s, nullptr, 0, index_dev, words))
-    return e;
-  cudaMemcpyAsync(top_scores_host, h->out_s.p, size_t(n_q) * k * 4, cudaMemcpyDeviceToHost, s);
-  cudaMemcpyAsync(top_ids_host, h->out_i.p, size_t(n_q) * k * 8, cudaMemcpyDeviceToHost, s);
-  cudaMemcpyAsync(top_counts_host, h->out_c.p, size_t(n_q) * 4, cudaMemcpyDeviceToHost, s);
-  return check_cuda(h, cudaStreamSynchronize(s), "search_host: stream sync");
+  const bool zc = h->zero_copy && m.rows <= 256 && out_bytes <= (64u << 10);
+  const size_t meta_off = 0, q_off = (m.host.size() + 255) & ~size_t(255), out_off = (q_off + q_bytes + 255) & ~size_t(255);
+  if (int e = reserve_pinned(h, h->stage, out_off + out_bytes)) return e;
+  uint8_t* st = static_cast<uint8_t*>(h->stage.p);
+  int e = 0;
+  if (zc) {
+    memcpy(st + meta_off, m.host.data(), m.host.size());
+    if (q_bytes) memcpy(st + q_off, q_host, q_bytes);
+    e = search_core(h, st + q_off, B200MS_F32, q_lens, n_q, k, allow_dev, i8_q_scale, score_scale, id_base,
+                    reinterpret_cast<float*>(st + out_off + out_scores_off), reinterpret_cast<int64_t*>(st + out_off + out_ids_off),
+                    reinterpret_cast<int32_t*>(st + out_off + out_counts_off), s, nullptr, index_dev, words, st + meta_off, &m);
+    if (e) return e;
+  } else {
+    if (int e2 = reserve(h, h->q_raw, q_bytes ? q_bytes : 512)) return e2;
+    if (int e2 = reserve(h, h->out_all, out_bytes)) return e2;
+    if (q_bytes)
+      if (int e2 = check_cuda(h, cudaMemcpyAsync(h->q_raw.p, q_host, q_bytes, cudaMemcpyHostToDevice, s), "search_host: H2D queries")) return e2;
+    uint8_t* od = static_cast<uint8_t*>(h->out_all.p);
+    e = search_core(h, h->q_raw.p, B200MS_F32, q_lens, n_q, k, allow_dev, i8_q_scale, score_scale, id_base,
+                    reinterpret_cast<float*>(od + out_scores_off), reinterpret_cast<int64_t*>(od + out_ids_off),
+                    reinterpret_cast<int32_t*>(od + out_counts_off), s, nullptr, index_dev, words, nullptr, &m);
+    if (e) return e;
+    if (int e2 = check_cuda(h, cudaMemcpyAsync(st + out_off, od, out_bytes, cudaMemcpyDeviceToHost, s), "search_host: D2H results")) return e2;
+  }
+  if (int e2 = check_cuda(h, cudaStreamSynchronize(s), "search_host: stream sync")) return e2;
+  memcpy(top_ids_host, st + out_off + out_ids_off, nk * 8);
+  memcpy(top_scores_host, st + out_off + out_scores_off, nk * 4);
+  memcpy(top_counts_host, st + out_off + out_counts_off, size_t(n_q) * 4);
+  return B200MS_OK;
 }
 
 B200MS_API int b200ms_search_host(b200ms_t* h, const float* q_host, const int32_t* q_lens, int n_q, int k,
@@ -634,64 +866,4 @@ B200MS_API int b200ms_search_host_masked(b200ms_t* h, const float* q_host, const
     return set_error(h, B200MS_EINVAL, "search_host_masked: n_masks > 0 needs the mask matrix and one index per query");
   return search_host_impl(h, q_host, q_lens, n_q, k, allow_masks_host, n_masks, mask_index_host, i8_q_scale, score_scale,
                           id_base, top_scores_host, top_ids_host, top_counts_host);
-}
-
-// ------------------------------------------------------------------------------------------------ FDE (next row f-1)
-B200MS_API int b200ms_fde_configure(b200ms_t* h, int reps, int ksim, int proj_dim, float scale, const float* simhash,
-                                    const int32_t* ams_index, const float* ams_sign) {
-  if (!h) return B200MS_EINVAL;
-  if (reps < 1 || ksim < 1 || ksim > 8 || proj_dim < 1 || proj_dim > 64 || (proj_dim << ksim) > 512 || ((proj_dim << ksim) % 8) ||
-      !simhash || !ams_index || !ams_sign)
-    return set_error(h, B200MS_EINVAL, "fde_configure: need 1<=ksim<=8, proj_dim<=64, proj_dim*2^ksim <= 512 and a multiple of 8");
-  for (int i = 0; i < reps * kDim; ++i)
-    if (ams_index[i] < 0 || ams_index[i] >= proj_dim) return set_error(h, B200MS_EINVAL, "fde_configure: ams_index out of range");
-  DeviceGuard g(h->device);
-  cudaStream_t s = h->stream;
-  if (int e = upload(h, h->fde_simhash, simhash, size_t(reps) * kDim * ksim * 4, s)) return e;
-  if (int e = upload(h, h->fde_ams_index, ams_index, size_t(reps) * kDim * 4, s)) return e;
-  if (int e = upload(h, h->fde_ams_sign, ams_sign, size_t(reps) * kDim * 4, s)) return e;
-  if (int e = check_cuda(h, cudaStreamSynchronize(s), "fde_configure: sync")) return e;
-  h->fde_reps = reps;
-  h->fde_ksim = ksim;
-  h->fde_proj = proj_dim;
-  h->fde_scale = scale;
-  h->fde_dim = reps * (1 << ksim) * proj_dim;
-  return B200MS_OK;
-}
-
-B200MS_API int64_t b200ms_fde_dim(const b200ms_t* h) { return h ? h->fde_dim : 0; }
-
-B200MS_API int b200ms_fde_encode(b200ms_t* h, const void* rows, int src_dtype, const int32_t* item_lens, int64_t n_items,
-                                 int is_document, float* out, void* stream) {
-  if (!h) return B200MS_EINVAL;
-  if (h->fde_dim == 0) return set_error(h, B200MS_ESTATE, "fde_encode: call b200ms_fde_configure first");
-  if (!src_dtype_ok(src_dtype) || n_items < 0 || n_items > 65535 || (n_items > 0 && (!rows || !item_lens || !out)))
-    return set_error(h, B200MS_EINVAL, "fde_encode: bad arguments (at most 65535 items per call)");
-  if (n_items == 0) return B200MS_OK;
-  DeviceGuard g(h->device);
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
-  std::vector<int64_t> st(size_t(n_items) + 1);
-  st[0] = 0;
-  for (int64_t i = 0; i < n_items; ++i) st[i + 1] = st[i] + (item_lens[i] > 0 ? item_lens[i] : 0);
-  if (int e = upload(h, h->meta_a, st.data(), st.size() * 8, s)) return e;
-  return launch_fde_encode(h, rows, src_dtype, static_cast<const int64_t*>(h->meta_a.p), int(n_items), is_document, out, s);
-}
-
-B200MS_API int b200ms_fde_finalize(b200ms_t* h, const float* fde, int64_t n, void* out_rows, float* inv_norm, void* stream) {
-  if (!h) return B200MS_EINVAL;
-  if (h->fde_dim == 0) return set_error(h, B200MS_ESTATE, "fde_finalize: call b200ms_fde_configure first");
-  if (n < 0 || (n > 0 && (!fde || !out_rows || !inv_norm))) return set_error(h, B200MS_EINVAL, "fde_finalize: bad arguments");
-  DeviceGuard g(h->device);
-  return launch_fde_finalize(h, fde, n, out_rows, inv_norm, static_cast<cudaStream_t>(stream));
-}
-
-B200MS_API int b200ms_fde_scan(b200ms_t* h, const void* fde_rows, const float* inv_norm, int64_t n_pages, const float* q_fde,
-                               int n_q, float* scores, int64_t ld, void* stream) {
-  if (!h) return B200MS_EINVAL;
-  if (h->fde_dim == 0) return set_error(h, B200MS_ESTATE, "fde_scan: call b200ms_fde_configure first");
-  if (n_pages < 0 || n_q < 0 || ld < n_pages || (n_pages > 0 && n_q > 0 && (!fde_rows || !inv_norm || !q_fde || !scores)) ||
-      (reinterpret_cast<uintptr_t>(fde_rows) & 15))
-    return set_error(h, B200MS_EINVAL, "fde_scan: bad arguments (rows 16-byte aligned, ld >= n_pages)");
-  DeviceGuard g(h->device);
-  return launch_fde_scan(h, fde_rows, inv_norm, n_pages, q_fde, n_q, scores, ld, static_cast<cudaStream_t>(stream));
 }

@@ -81,7 +81,7 @@ maxsim_b1_kernel(const uint4* __restrict__ rows, const int64_t* __restrict__ pag
 }
 
 int launch_score_b1(b200ms_t* h, const int64_t* cand_ids, int64_t n_cand, const void* q_packed, int n_groups,
-                    const int32_t* group_ntok_dev, void* group_scores, int64_t ld, cudaStream_t s) {
+                    const int32_t* group_ntok_dev, void* group_scores, int64_t ld, cudaStream_t s, int g_lo, int g_hi) {
   const Corpus& c = h->corpus;
   const int64_t n_items = cand_ids ? n_cand : c.n_pages;
   if (n_items == 0 || n_groups == 0) return B200MS_OK;
@@ -92,8 +92,11 @@ int launch_score_b1(b200ms_t* h, const int64_t* cand_ids, int64_t n_cand, const 
   const int64_t* ps = static_cast<const int64_t*>(h->page_start.p);
   const uint4* qb = static_cast<const uint4*>(q_packed);
   int32_t* out = static_cast<int32_t*>(group_scores);
-  for (int base = 0; base < n_groups;) {
-    const int rem = n_groups - base;
+  // groups [g_lo, g_hi) only (the batched rerank scores each query against its own candidate list)
+  if (g_hi > n_groups) g_hi = n_groups;
+  n_groups = g_hi;  // the kernels treat groups >= n_groups as absent
+  for (int base = g_lo; base < g_hi;) {
+    const int rem = g_hi - base;
     if (rem >= 8) {
       maxsim_b1_kernel<8><<<grid, kB1Warps * 32, 0, s>>>(rows, ps, n_items, cand_ids, qb, group_ntok_dev, base, n_groups, out, ld);
       base += 8;

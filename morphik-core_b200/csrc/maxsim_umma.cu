@@ -14,6 +14,10 @@
 //                 4 groups = 128 query tokens; TMEM lane i of the accumulator = query token i of the tile
 //   scores        group_scores[g, p] (f32 | s32), g = 32-token group, p = page
 //
+// Kernels here: maxsim_umma_kernel<KIND,NM=1|2> (384 threads, two epilogue warpgroups) and maxsim_umma_w4_kernel<KIND,NM=4|8>
+// (640 threads, four epilogue warpgroups).  The batch regime normally runs on CTA pairs (maxsim_umma_pair.cu); the round-1
+// variants that lost their A/B (query operand from TMEM, replicated-query "split4" epilogue, two-warpgroup NM >= 4) are gone.
+// KIND: 0 bf16, 1 int8, 2 fp8 e4m3 (umma_tile.cuh).
 // Kernel (persistent, one CTA per SM, 384 threads, warp-specialised):
 //   warp 0      TMA producer: streams 128-row patch tiles (SWIZZLE_128B boxes) through an S-stage mbarrier ring
 //   warp 1      MMA issuer: for every patch tile and every resident query tile m < NM issues the K=128
@@ -31,35 +35,26 @@
 namespace bms {
 
 constexpr int kThreads = 384;
-// AT = false: A (queries) from shared memory, 4 accumulators of 128 columns          ("SS" form)
-// AT = true : A (queries) staged ONCE into TMEM columns [0, 64*NM) by tcgen05.st and fed from there ("TS" form), 4
-//             accumulators of 64 columns at [256, 512): the tensor core then reads only B from shared memory
-//             (64 B/clk instead of 128 B/clk at the nominal MMA rate) and the query tiles free 32 KB * NM of smem.
-// S4 (NM == 1, SS form, ONE 32-token group -- the single-query case): the 32 query rows are TMA-loaded into all four
-//             32-row quarters of the tile, so every lane quadrant of the accumulator holds the same tokens and each of the
-//             four epilogue warps reduces one 32-column chunk in parallel (instead of warp 0 walking all four); the chunk
-//             maxima meet in a shared-memory slab once per tile and warp 0 applies the page logic.
-template <int KIND, int NM, bool AT, bool S4>
+
+// One CTA per SM, NM = 1 or 2 resident query tiles, two epilogue warpgroups (warpgroup e owns query tiles m == e mod 2;
+// at NM = 1 only warpgroup 0 works).  The lone-query / rerank kernel: HBM-bound while NM * 128 <= ~256 query tokens.
+template <int KIND, int NM>
 __global__ void __launch_bounds__(kThreads, 1)
 maxsim_umma_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constant__ CUtensorMap tmap_q,
-                   const void* __restrict__ q_rows, int n_q_rows, const int32_t* __restrict__ chunk_page,
-                   const int32_t* __restrict__ unit_start, const int32_t* __restrict__ unit_end, int slot_mode,
-                   int n_units, int m_tile_base, int n_groups_real,
-                   typename Kind<KIND>::Acc* __restrict__ group_scores, int64_t ld, int num_stages) {
+                   const int32_t* __restrict__ chunk_page, const int32_t* __restrict__ unit_start,
+                   const int32_t* __restrict__ unit_end, int slot_mode, int n_units, int m_tile_base, int n_groups_real,
+                   const uint32_t* __restrict__ clamp_bits, typename Kind<KIND>::Acc* __restrict__ group_scores, int64_t ld,
+                   int num_stages) {
   using K = Kind<KIND>;
   using Acc = typename K::Acc;
-  constexpr int NWG = NM == 1 ? 1 : 2;        // epilogue warpgroups in use
-  constexpr int NMW = NM == 1 ? 1 : NM / 2;   // query tiles owned by one epilogue warpgroup
-  constexpr int kAccN = AT ? 64 : 128;        // columns (= patch rows) per accumulator
-  constexpr int kHalves = kTileN / kAccN;     // accumulators per (patch tile, query tile)
-  constexpr int kAccCol0 = AT ? 256 : 0;      // first accumulator column
-  constexpr int kQCols = KIND == 0 ? 64 : 32; // TMEM columns of one query tile (128 x 128 elements, 4 B per column)
-  constexpr int kKSteps = KIND == 0 ? 8 : 4;  // tcgen05.mma K steps per tile (32 B of K each)
+  static_assert(NM == 1 || NM == 2, "two-warpgroup form: 1 or 2 query tiles (4 and 8 run on maxsim_umma_w4_kernel)");
+  constexpr int NWG = NM;                      // epilogue warpgroups in use
+  constexpr int kKSteps = K::kKSteps;          // tcgen05.mma K steps per tile (32 B of K each)
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* smem_q = smem;                                            // NM query tiles (SS form only)
-  uint8_t* smem_st = smem + (AT ? 0 : NM * K::kTileBytes);           // num_stages patch tiles
+  uint8_t* smem_q = smem;                                            // NM query tiles
+  uint8_t* smem_st = smem + NM * K::kTileBytes;                      // num_stages patch tiles
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_st + size_t(num_stages) * K::kTileBytes);
   uint64_t* full = bars;                     // [num_stages] TMA -> MMA
   uint64_t* empty = bars + 16;               // [num_stages] MMA -> TMA
@@ -67,14 +62,13 @@ maxsim_umma_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_c
   uint64_t* tempty = bars + 40;              // [kNumAccum]  epilogue -> MMA
   uint64_t* qfull = bars + 48;               // query tiles landed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 56);
-  uint32_t* slab = reinterpret_cast<uint32_t*>(bars + 64);  // S4: [2][4][32] chunk maxima (raw bits)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_rows);
-    if (!AT) prefetch_tmap(&tmap_q);
+    prefetch_tmap(&tmap_q);
     for (int i = 0; i < num_stages; ++i) {
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], 1);
@@ -83,7 +77,7 @@ maxsim_umma_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_c
       mbar_init(&tfull[i], 1);
       mbar_init(&tempty[i], 4);  // one arrive per epilogue warp of the owning warpgroup
     }
-    mbar_init(qfull, AT ? 4 : 1);
+    mbar_init(qfull, 1);
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc_512(tmem_slot);
@@ -96,24 +90,14 @@ maxsim_umma_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_c
     // ================================================================ TMA producer
     if (lane == 0) {
       const uint64_t pol_rows = policy_evict_first();
-      if constexpr (!AT) {
-        const uint64_t pol_q = policy_evict_last();
-        mbar_expect_tx(qfull, NM * K::kTileBytes);
-        if constexpr (S4) {  // tmap_q has 32-row boxes: the group's 32 token rows land in all four row quarters
+      const uint64_t pol_q = policy_evict_last();
+      mbar_expect_tx(qfull, NM * K::kTileBytes);
 #pragma unroll
-          for (int p = 0; p < K::kPanels; ++p)
+      for (int m = 0; m < NM; ++m)
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-              tma_load_2d(&tmap_q, qfull, smem_q + p * kSubtileBytes + j * 4096, p * K::kPanelElems, m_tile_base * kTileM, pol_q);
-        } else {
-#pragma unroll
-          for (int m = 0; m < NM; ++m)
-#pragma unroll
-            for (int p = 0; p < K::kPanels; ++p)
-              tma_load_2d(&tmap_q, qfull, smem_q + m * K::kTileBytes + p * kSubtileBytes, p * K::kPanelElems,
-                          (m_tile_base + m) * kTileM, pol_q);
-        }
-      }
+        for (int p = 0; p < K::kPanels; ++p)
+          tma_load_2d(&tmap_q, qfull, smem_q + m * K::kTileBytes + p * kSubtileBytes, p * K::kPanelElems,
+                      (m_tile_base + m) * kTileM, pol_q);
       int stage = 0;
       uint32_t phase = 0;
       for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
@@ -138,7 +122,7 @@ maxsim_umma_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_c
     // ================================================================ MMA issuer
     // The whole warp walks the loop (so every address/descriptor is warp-uniform and lives in uniform registers);
     // only the tcgen05.mma / tcgen05.commit themselves are issued by the lane elect.sync picks.
-    constexpr uint32_t idesc = umma_idesc(KIND, kTileM, kAccN);
+    constexpr uint32_t idesc = umma_idesc(KIND, kTileM, kTileN);
     constexpr uint32_t kTileDesc = K::kTileBytes >> 4;  // tile size in descriptor units (16 B)
     mbar_wait(qfull, 0);
     tc_fence_after();
@@ -155,34 +139,21 @@ maxsim_umma_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_c
         tc_fence_after();
         const uint64_t bd = b_desc0 + uint64_t(uint32_t(stage) * kTileDesc);
 #pragma unroll 1
-        for (int m = 0; m < NM; ++m) {
+        for (int m = 0; m < NM; ++m, ++seq) {
+          const uint32_t buf = seq & (kNumAccum - 1);
+          mbar_wait(&tempty[buf], ((seq >> 2) & 1) ^ 1);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t d_tmem = tmem_base + buf * kTileN;
+            const uint64_t ad = a_desc0 + uint64_t(uint32_t(m) * kTileDesc);
 #pragma unroll
-          for (int hf = 0; hf < kHalves; ++hf, ++seq) {
-            const uint32_t buf = seq & (kNumAccum - 1);
-            mbar_wait(&tempty[buf], ((seq >> 2) & 1) ^ 1);
-            tc_fence_after();
-            if (elect_one()) {
-              const uint32_t d_tmem = tmem_base + kAccCol0 + buf * kAccN;
-              if constexpr (AT) {
-                const uint32_t a_tmem = tmem_base + uint32_t(m) * kQCols;
-                const uint64_t bh = bd + uint64_t((hf * kAccN * 128) >> 4);  // rows hf*64.. of every 128 B panel
-#pragma unroll
-                for (int ks = 0; ks < kKSteps; ++ks) {
-                  const uint32_t off = ((ks >> 2) * kSubtileBytes + (ks & 3) * 32) >> 4;
-                  umma_ts<KIND>(d_tmem, a_tmem + ks * 8, bh + off, idesc, ks != 0);
-                }
-              } else {
-                const uint64_t ad = a_desc0 + uint64_t(uint32_t(m) * kTileDesc);
-#pragma unroll
-                for (int ks = 0; ks < kKSteps; ++ks) {  // 32 B of K per step; 4 steps per 128 B panel
-                  const uint32_t off = ((ks >> 2) * kSubtileBytes + (ks & 3) * 32) >> 4;
-                  umma_ss<KIND>(d_tmem, ad + off, bd + off, idesc, ks != 0);
-                }
-              }
-              umma_commit(&tfull[buf]);
+            for (int ks = 0; ks < kKSteps; ++ks) {  // 32 B of K per step; 4 steps per 128 B panel
+              const uint32_t off = ((ks >> 2) * kSubtileBytes + (ks & 3) * 32) >> 4;
+              umma_ss<KIND>(d_tmem, ad + off, bd + off, idesc, ks != 0);
             }
-            __syncwarp();
+            umma_commit(&tfull[buf]);
           }
+          __syncwarp();
         }
         if (elect_one()) umma_commit(&empty[stage]);  // stage reusable once every query tile has consumed it
         __syncwarp();
@@ -197,185 +168,69 @@ maxsim_umma_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_c
     const int wg = (warp - 4) >> 2;
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
     const uint32_t lane_base = tmem_base + (uint32_t(quad * 32) << 16);
-
-    if constexpr (AT) {
-      // Stage the query tiles into TMEM once: thread (quad, lane) owns token row quad*32+lane of every tile and writes its
-      // 256 B (bf16) / 128 B (s8) as consecutive 32-bit columns -- the K-major A layout tcgen05.mma reads from TMEM.
-      if (wg == 0) {
-        const int row_in_tile = quad * 32 + lane;
-#pragma unroll 1
-        for (int m = 0; m < NM; ++m) {
-          const int64_t row = int64_t(m_tile_base + m) * kTileM + row_in_tile;
-          const bool live = row < n_q_rows;
-#pragma unroll
-          for (int c = 0; c < kQCols; c += 32) {
-            uint32_t v[32];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              uint4 w = make_uint4(0, 0, 0, 0);
-              if (live) w = __ldg(reinterpret_cast<const uint4*>(static_cast<const uint8_t*>(q_rows) + row * (kQCols * 4)) + (c >> 2) + j);
-              v[4 * j] = w.x;
-              v[4 * j + 1] = w.y;
-              v[4 * j + 2] = w.z;
-              v[4 * j + 3] = w.w;
-            }
-            tmem_st_32x32(lane_base + m * kQCols + c, v);
-          }
-        }
-        tmem_st_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(qfull);
-      }
-    }
-
-    if constexpr (S4) {
-      if (wg == 0) {
-        const int group = m_tile_base * 4;
-        Acc rm = Acc(0);
-        int cp = -1;
-        uint32_t seq = 0;
-        for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
-          const int c0 = __ldg(unit_start + u), c1 = __ldg(unit_end + u);
-          const int n_tiles = (c1 - c0 + 3) >> 2;
-          for (int t = 0; t < n_tiles; ++t, ++seq) {
-            const uint32_t buf = seq & (kNumAccum - 1);
-            mbar_wait(&tfull[buf], (seq >> 2) & 1);
-            tc_fence_after();
-            uint32_t va[32];
-            tmem_ld_32x32(lane_base + kAccCol0 + buf * kAccN + quad * 32, va);  // chunk `quad` of this quadrant's copy
-            tmem_ld_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[buf]);
-            uint32_t* sl = slab + (seq & 1) * 128;
-            const Acc mine = chunk_max<Acc>(va);
-            sl[quad * 32 + lane] = *reinterpret_cast<const uint32_t*>(&mine);
-            asm volatile("bar.sync 1, 128;" ::: "memory");  // the four warps of epilogue warpgroup 0
-            if (quad == 0) {
-              const int cb = c0 + 4 * t;
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                if (cb + j >= c1) break;
-                const int pgj = __ldg(chunk_page + cb + j);
-                const Acc v = acc_from_bits(sl[j * 32 + lane], Acc{});
-                if (pgj != cp) {
-                  if (cp >= 0) {
-                    const Acc s2 = warp_sum(rm);
-                    if (lane == 0) group_scores[int64_t(group) * ld + (slot_mode ? u : cp)] = s2;
-                  }
-                  cp = pgj;
-                  rm = v;
-                } else {
-                  rm = acc_max(rm, v);
-                }
-              }
-            }
-          }
-          if (quad == 0 && cp >= 0) {  // unit ends on a page boundary
-            const Acc s2 = warp_sum(rm);
-            if (lane == 0) group_scores[int64_t(group) * ld + (slot_mode ? u : cp)] = s2;
-          }
-          cp = -1;
-        }
-      }
-    } else if (wg < NWG) {
-      Acc runmax[NMW];
-      int cur_page[NMW];
+    if (wg < NWG) {
+      const int m = wg;  // the query tile this warpgroup owns
+      const int group = (m_tile_base + m) * 4 + quad;
+      const bool active = group < n_groups_real;
+      Acc rm = Acc(0);
+      int cp = -1;
       uint32_t tile_seq = 0;
-
       for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
         const int c0 = __ldg(unit_start + u), c1 = __ldg(unit_end + u);
         const int n_tiles = (c1 - c0 + 3) >> 2;
-#pragma unroll
-        for (int i = 0; i < NMW; ++i) cur_page[i] = -1;
-
+        cp = -1;
         for (int t = 0; t < n_tiles; ++t, ++tile_seq) {
           const int cb = c0 + 4 * t;
           int pg[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) pg[j] = (cb + j < c1) ? __ldg(chunk_page + cb + j) : -1;
-
-          // one code copy for all owned query tiles (runtime loop): the per-tile state is moved in and out of the
-          // register arrays with compile-time-indexed selects, which keeps them out of local memory
-#pragma unroll 1
-          for (int i = 0; i < NMW; ++i) {
-            const int m = NM == 1 ? 0 : (2 * i + wg);
-            const uint32_t seq0 = (tile_seq * NM + m) * kHalves;
-            const int group = (m_tile_base + m) * 4 + quad;
-            const bool active = group < n_groups_real;
-            Acc rm = Acc(0);
-            int cp = -1;
-#pragma unroll
-            for (int j = 0; j < NMW; ++j)
-              if (j == i) {
-                rm = runmax[j];
-                cp = cur_page[j];
-              }
+          const uint32_t seq = tile_seq * NM + m;
+          const uint32_t buf = seq & (kNumAccum - 1);
+          mbar_wait(&tfull[buf], (seq >> 2) & 1);
+          tc_fence_after();
+          if (active) {
+            const uint32_t taddr = lane_base + buf * kTileN;
+            uint32_t va[32], vb[32];
             Acc cm[4];
+            tmem_ld_32x32(taddr, va);
+            tmem_ld_32x32(taddr + 32, vb);
+            tmem_ld_wait();
+            cm[0] = chunk_max<Acc>(va);
+            cm[1] = chunk_max<Acc>(vb);
+            tmem_ld_32x32(taddr + 64, va);
+            tmem_ld_32x32(taddr + 96, vb);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[buf]);  // accumulator drained: MMA may overwrite it
+            cm[2] = chunk_max<Acc>(va);
+            cm[3] = chunk_max<Acc>(vb);
 #pragma unroll
-            for (int hf = 0; hf < kHalves; ++hf) {
-              const uint32_t seq = seq0 + hf;
-              const uint32_t buf = seq & (kNumAccum - 1);
-              mbar_wait(&tfull[buf], (seq >> 2) & 1);
-              tc_fence_after();
-              if (active) {
-                const uint32_t taddr = lane_base + kAccCol0 + buf * kAccN;
-                uint32_t va[32], vb[32];
-                tmem_ld_32x32(taddr, va);
-                tmem_ld_32x32(taddr + 32, vb);
-                tmem_ld_wait();
-                if constexpr (kHalves == 1) {
-                  cm[0] = chunk_max<Acc>(va);
-                  cm[1] = chunk_max<Acc>(vb);
-                  tmem_ld_32x32(taddr + 64, va);
-                  tmem_ld_32x32(taddr + 96, vb);
-                  tmem_ld_wait();
+            for (int j = 0; j < 4; ++j) {
+              if (pg[j] < 0) continue;  // chunk belongs to the next unit
+              if (pg[j] != cp) {
+                if (cp >= 0) {
+                  const int o = slot_mode ? u : cp;
+                  const Acc s = warp_sum(clamp_token_max(clamp_bits, o, rm));
+                  if (lane == 0) group_scores[int64_t(group) * ld + o] = s;
                 }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&tempty[buf]);  // accumulator drained: MMA may overwrite it
-                cm[kHalves == 1 ? 2 : 2 * hf] = chunk_max<Acc>(va);
-                cm[kHalves == 1 ? 3 : 2 * hf + 1] = chunk_max<Acc>(vb);
+                cp = pg[j];
+                rm = cm[j];
               } else {
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&tempty[buf]);
+                rm = acc_max(rm, cm[j]);
               }
             }
-            if (active) {
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                if (pg[j] < 0) continue;  // chunk belongs to the next unit
-                if (pg[j] != cp) {
-                  if (cp >= 0) {
-                    const Acc s = warp_sum(rm);
-                    if (lane == 0) group_scores[int64_t(group) * ld + (slot_mode ? u : cp)] = s;
-                  }
-                  cp = pg[j];
-                  rm = cm[j];
-                } else {
-                  rm = acc_max(rm, cm[j]);
-                }
-              }
-            }
-#pragma unroll
-            for (int j = 0; j < NMW; ++j)
-              if (j == i) {
-                runmax[j] = rm;
-                cur_page[j] = cp;
-              }
+          } else {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[buf]);
           }
         }
-        // unit ends on a page boundary: flush the open page of every owned query tile
-#pragma unroll
-        for (int i = 0; i < NMW; ++i) {
-          const int m = NM == 1 ? 0 : (2 * i + wg);
-          const int group = (m_tile_base + m) * 4 + quad;
-          if (group < n_groups_real && cur_page[i] >= 0) {
-            const Acc s = warp_sum(runmax[i]);
-            if (lane == 0) group_scores[int64_t(group) * ld + (slot_mode ? u : cur_page[i])] = s;
-          }
+        // unit ends on a page boundary: flush the open page
+        if (active && cp >= 0) {
+          const int o = slot_mode ? u : cp;
+          const Acc s = warp_sum(clamp_token_max(clamp_bits, o, rm));
+          if (lane == 0) group_scores[int64_t(group) * ld + o] = s;
         }
       }
     }
@@ -401,12 +256,13 @@ __global__ void __launch_bounds__(kThreadsW4, 1)
 maxsim_umma_w4_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constant__ CUtensorMap tmap_q,
                       const int32_t* __restrict__ chunk_page, const int32_t* __restrict__ unit_start,
                       const int32_t* __restrict__ unit_end, int slot_mode, int n_units, int m_tile_base, int n_groups_real,
-                      typename Kind<KIND>::Acc* __restrict__ group_scores, int64_t ld, int num_stages) {
+                      const uint32_t* __restrict__ clamp_bits, typename Kind<KIND>::Acc* __restrict__ group_scores, int64_t ld,
+                      int num_stages) {
   using K = Kind<KIND>;
   using Acc = typename K::Acc;
   static_assert(NM % 4 == 0, "W4 form needs a multiple of four query tiles");
   constexpr int MPW = NM / 4;                  // query tiles per epilogue warpgroup
-  constexpr int kKSteps = KIND == 0 ? 8 : 4;
+  constexpr int kKSteps = K::kKSteps;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -562,8 +418,9 @@ maxsim_umma_w4_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __gri
               if (pg[j] < 0) continue;
               if (pg[j] != cur_page[i]) {
                 if (cur_page[i] >= 0) {
-                  const Acc s2 = warp_sum(runmax[i]);
-                  if (lane == 0) group_scores[int64_t(group) * ld + (slot_mode ? u : cur_page[i])] = s2;
+                  const int o = slot_mode ? u : cur_page[i];
+                  const Acc s2 = warp_sum(clamp_token_max(clamp_bits, o, runmax[i]));
+                  if (lane == 0) group_scores[int64_t(group) * ld + o] = s2;
                 }
                 cur_page[i] = pg[j];
                 runmax[i] = cm[j];
@@ -582,8 +439,9 @@ maxsim_umma_w4_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __gri
       for (int i = 0; i < MPW; ++i) {
         const int group = (m_tile_base + wg + 4 * i) * 4 + quad;
         if (group < n_groups_real && cur_page[i] >= 0) {
-          const Acc s2 = warp_sum(runmax[i]);
-          if (lane == 0) group_scores[int64_t(group) * ld + (slot_mode ? u : cur_page[i])] = s2;
+          const int o = slot_mode ? u : cur_page[i];
+          const Acc s2 = warp_sum(clamp_token_max(clamp_bits, o, runmax[i]));
+          if (lane == 0) group_scores[int64_t(group) * ld + o] = s2;
         }
       }
     }
@@ -615,53 +473,50 @@ static int launch_w4(b200ms_t* h, const UnitPlan& up, const CUtensorMap& tq, int
   if (grid > up.n_units) grid = up.n_units;
   if (grid < 1) return B200MS_OK;
   kern<<<grid, kThreadsW4, smem, s>>>(c.tmap, tq, static_cast<const int32_t*>(h->chunk_page.p), up.start, up.end, up.slot_mode,
-                                     up.n_units, m_tile_base, n_groups_real, static_cast<typename K::Acc*>(scores), ld, stages);
+                                     up.n_units, m_tile_base, n_groups_real, up.clamp_bits,
+                                     static_cast<typename K::Acc*>(scores), ld, stages);
   h->launches++;
   return check_cuda(h, cudaGetLastError(), "launch maxsim_umma_w4");
 }
 
 // ---------------------------------------------------------------------------------------------- host side
-template <int KIND, int NM, bool AT, bool S4 = false>
-static int launch_one(b200ms_t* h, const UnitPlan& up, const CUtensorMap& tq, const void* q_rows, int n_q_rows,
-                      int m_tile_base, int n_groups_real, void* scores, int64_t ld, cudaStream_t s) {
+template <int KIND, int NM>
+static int launch_one(b200ms_t* h, const UnitPlan& up, const CUtensorMap& tq, int m_tile_base, int n_groups_real,
+                      void* scores, int64_t ld, cudaStream_t s) {
   using K = Kind<KIND>;
   const Corpus& c = h->corpus;
-  const uint32_t q_bytes = AT ? 0 : NM * K::kTileBytes;
-  const uint32_t avail = kSmemLimit - 1024 /*align*/ - kBarrierBytes - q_bytes;
+  const uint32_t avail = kSmemLimit - 1024 /*align*/ - kBarrierBytes - NM * K::kTileBytes;
   int stages = int(avail / K::kTileBytes);
   if (stages > 8) stages = 8;
-  if (stages < 2) return set_error(h, B200MS_EINVAL, "maxsim_umma: not enough shared memory for 2 stages");
-  const uint32_t smem = 1024 + q_bytes + uint32_t(stages) * K::kTileBytes + kBarrierBytes;
-  auto kern = maxsim_umma_kernel<KIND, NM, AT, S4>;
+  const uint32_t smem = 1024 + NM * K::kTileBytes + uint32_t(stages) * K::kTileBytes + kBarrierBytes;
+  auto kern = maxsim_umma_kernel<KIND, NM>;
   if (int e = check_cuda(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)),
                          "cudaFuncSetAttribute(maxsim_umma)"))
     return e;
   int grid = h->max_ctas > 0 ? h->max_ctas : h->num_sms;
   if (grid > up.n_units) grid = up.n_units;
   if (grid < 1) return B200MS_OK;
-  kern<<<grid, kThreads, smem, s>>>(c.tmap, tq, q_rows, n_q_rows, static_cast<const int32_t*>(h->chunk_page.p), up.start,
-                                   up.end, up.slot_mode, up.n_units, m_tile_base, n_groups_real,
+  kern<<<grid, kThreads, smem, s>>>(c.tmap, tq, static_cast<const int32_t*>(h->chunk_page.p), up.start, up.end, up.slot_mode,
+                                   up.n_units, m_tile_base, n_groups_real, up.clamp_bits,
                                    static_cast<typename K::Acc*>(scores), ld, stages);
   h->launches++;
   return check_cuda(h, cudaGetLastError(), "launch maxsim_umma");
 }
 
-template <int KIND, bool AT>
-static int launch_kind(b200ms_t* h, const UnitPlan& up, const CUtensorMap& tq, const void* q_rows, int n_q_rows,
-                       int n_groups_real, int n_mtiles, void* scores, int64_t ld, cudaStream_t s) {
-  // resident query tiles per pass: SS form is bounded by shared memory (bf16 4, s8 8), TS form by the 256 TMEM columns
-  // left of the accumulators (bf16 4 x 64 columns, s8 8 x 32 columns)
-  constexpr int kMaxNM = KIND == 0 ? 4 : 8;
+// Pass planner: score query tiles [0, n_mtiles) against the unit plan with as few passes over the corpus as possible.
+//   CTA-pair forms (maxsim_umma_pair.cu) hold 2*per query tiles per pass; pick the largest per whose phantom (zero) tiles
+//   stay below a quarter of the pass -- 5 tiles run as 4 + 1, not as 8 (measured per pass at 32768 pages: 8 tiles 5.08 ms,
+//   4 tiles ~2.5 ms, one tile 1.28 ms); pair_cta = 2 (default) also sends exactly two tiles to the two-tile pair kernel.
+//   One-CTA forms: a single tile (the lone query, HBM-bound) always; 2 / 4 / 8 tiles only where CTA pairs cannot be
+//   co-scheduled (pair_cta = 0 or a partition without whole TPCs) -- same results, bit for bit.
+template <int KIND>
+static int launch_kind(b200ms_t* h, const UnitPlan& up, const CUtensorMap& tq, int n_groups_real, int n_mtiles, void* scores,
+                       int64_t ld, cudaStream_t s) {
+  constexpr int kMaxNM = Kind<KIND>::kMaxNM;
   int base = 0;
   while (base < n_mtiles) {
     const int rem = n_mtiles - base;
-    int nm = 1;
-    while (nm < rem && nm < kMaxNM) nm <<= 1;  // round up: a phantom (all-zero) tile beats a 2nd pass over the corpus
-    int e;
-    if (!AT && h->pair_cta && rem >= (h->pair_cta >= 2 ? 2 : 3)) {
-      // CTA-pair forms: 2*per query tiles per pass.  Pick the largest per whose phantom (zero) tiles stay below a quarter
-      // of the pass -- 5 tiles run as 4 + 1, not as 8 (measured per pass at 32768 pages: 8 tiles 5.08 ms, 4 tiles ~2.5 ms,
-      // one tile 1.28 ms); pair_cta = 2 also sends exactly two tiles to the two-tile pair kernel.
+    if (h->pair_cta && rem >= (h->pair_cta >= 2 ? 2 : 3)) {
       int per = kMaxNM;
       while (per > 1 && rem < 2 * per - (per >= 4 ? per / 4 : 1)) per >>= 1;
       if (per == 1 && (h->pair_cta < 2 || rem < 2)) per = 0;
@@ -675,25 +530,16 @@ static int launch_kind(b200ms_t* h, const UnitPlan& up, const CUtensorMap& tq, c
         h->pair_cta = 0;  // e.g. a partition without whole TPCs: the one-CTA kernels below do the same work
       }
     }
-    if (!AT && h->epi_w4 && nm >= 4) {  // four-epilogue-warpgroup form
-      if (nm == 4) {
-        e = launch_w4<KIND, 4>(h, up, tq, base, n_groups_real, scores, ld, s);
-      } else if constexpr (KIND == 1) {
-        e = launch_w4<KIND, 8>(h, up, tq, base, n_groups_real, scores, ld, s);
-      } else {
-        e = set_error(h, B200MS_EINVAL, "maxsim_umma_w4: bad NM");
-      }
-      if (e) return e;
-      base += nm;
-      continue;
-    }
+    int nm = 1;
+    while (nm < rem && nm < kMaxNM) nm <<= 1;  // round up: a phantom (all-zero) tile beats a 2nd pass over the corpus
+    int e;
     switch (nm) {
-      case 1: e = launch_one<KIND, 1, AT>(h, up, tq, q_rows, n_q_rows, base, n_groups_real, scores, ld, s); break;
-      case 2: e = launch_one<KIND, 2, AT>(h, up, tq, q_rows, n_q_rows, base, n_groups_real, scores, ld, s); break;
-      case 4: e = launch_one<KIND, 4, AT>(h, up, tq, q_rows, n_q_rows, base, n_groups_real, scores, ld, s); break;
+      case 1: e = launch_one<KIND, 1>(h, up, tq, base, n_groups_real, scores, ld, s); break;
+      case 2: e = launch_one<KIND, 2>(h, up, tq, base, n_groups_real, scores, ld, s); break;
+      case 4: e = launch_w4<KIND, 4>(h, up, tq, base, n_groups_real, scores, ld, s); break;
       default:
-        if constexpr (KIND == 1) {
-          e = launch_one<KIND, 8, AT>(h, up, tq, q_rows, n_q_rows, base, n_groups_real, scores, ld, s);
+        if constexpr (kMaxNM >= 8) {
+          e = launch_w4<KIND, 8>(h, up, tq, base, n_groups_real, scores, ld, s);
         } else {
           e = set_error(h, B200MS_EINVAL, "maxsim_umma: bad NM");
         }
@@ -704,8 +550,10 @@ static int launch_kind(b200ms_t* h, const UnitPlan& up, const CUtensorMap& tq, c
   return B200MS_OK;
 }
 
+// m_tile_lo / m_tile_hi: score only query tiles [m_tile_lo, m_tile_hi) (hi < 0: all) -- the batched rerank walks the query
+// tiles one launch at a time, each against its own candidate units.
 int launch_score_umma(b200ms_t* h, const UnitPlan* plan, const void* q_packed, int n_groups_real, void* group_scores,
-                      int64_t ld, cudaStream_t s) {
+                      int64_t ld, cudaStream_t s, int m_tile_lo, int m_tile_hi) {
   const Corpus& c = h->corpus;
   UnitPlan up;
   if (plan) {
@@ -720,25 +568,25 @@ int launch_score_umma(b200ms_t* h, const UnitPlan* plan, const void* q_packed, i
   const int n_groups_padded = (n_groups_real + 3) & ~3;
   const int n_mtiles = n_groups_padded / 4;
   const int n_q_rows = n_groups_padded * kGroup;
-  const bool ts = h->a_in_tmem != 0;
-  // Single 32-token group: optional replicated-query form (32-row TMA boxes).  In short runs it is 5 % faster for bf16
-  // (2.40 vs 2.51-2.59 ms at 65536 pages) but it makes the tensor cores multiply four copies of real data instead of
-  // 96 zero rows, and under the sustained 1 kW power cap of bench.py that costs 7 % of HBM throughput (6.0 vs 6.5 TB/s,
-  // A/B on one box) -- so it is OFF by default (split4 = 0); 1 enables it for bf16, 2 for every dtype.
-  if (!ts && n_groups_real == 1 && (h->split4 == 2 || (h->split4 == 1 && c.dtype == B200MS_BF16))) {
-    if (int e = make_tmap_rows(h, &h->tmap_q, q_packed, c.dtype, int64_t(n_q_rows), 32)) return e;
-    return c.dtype == B200MS_BF16
-               ? launch_one<0, 1, false, true>(h, up, h->tmap_q, q_packed, n_q_rows, 0, n_groups_real, group_scores, ld, s)
-               : launch_one<1, 1, false, true>(h, up, h->tmap_q, q_packed, n_q_rows, 0, n_groups_real, group_scores, ld, s);
+  if (int e = make_tmap_rows(h, &h->tmap_q, q_packed, c.dtype, int64_t(n_q_rows), kTileM)) return e;
+  if (m_tile_hi >= 0) {  // one explicit tile range: the single-tile kernel per tile (candidate lists are short)
+    for (int m = m_tile_lo; m < m_tile_hi && m < n_mtiles; ++m) {
+      int e;
+      switch (kind_of_dtype(c.dtype)) {
+        case 0: e = launch_one<0, 1>(h, up, h->tmap_q, m, n_groups_real, group_scores, ld, s); break;
+        case 1: e = launch_one<1, 1>(h, up, h->tmap_q, m, n_groups_real, group_scores, ld, s); break;
+        default: e = launch_one<2, 1>(h, up, h->tmap_q, m, n_groups_real, group_scores, ld, s); break;
+      }
+      if (e) return e;
+    }
+    return B200MS_OK;
   }
-  if (!ts)
-    if (int e = make_tmap_rows(h, &h->tmap_q, q_packed, c.dtype, int64_t(n_q_rows), kTileM)) return e;
-  if (c.dtype == B200MS_BF16) {
-    return ts ? launch_kind<0, true>(h, up, h->tmap_q, q_packed, n_q_rows, n_groups_real, n_mtiles, group_scores, ld, s)
-              : launch_kind<0, false>(h, up, h->tmap_q, q_packed, n_q_rows, n_groups_real, n_mtiles, group_scores, ld, s);
+  switch (kind_of_dtype(c.dtype)) {
+    case 0: return launch_kind<0>(h, up, h->tmap_q, n_groups_real, n_mtiles, group_scores, ld, s);
+    case 1: return launch_kind<1>(h, up, h->tmap_q, n_groups_real, n_mtiles, group_scores, ld, s);
+    case 2: return launch_kind<2>(h, up, h->tmap_q, n_groups_real, n_mtiles, group_scores, ld, s);
+    default: return set_error(h, B200MS_ESTATE, "score: corpus dtype has no tcgen05 scorer");
   }
-  return ts ? launch_kind<1, true>(h, up, h->tmap_q, q_packed, n_q_rows, n_groups_real, n_mtiles, group_scores, ld, s)
-            : launch_kind<1, false>(h, up, h->tmap_q, q_packed, n_q_rows, n_groups_real, n_mtiles, group_scores, ld, s);
 }
 
 }  // namespace bms

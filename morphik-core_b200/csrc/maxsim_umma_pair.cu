@@ -34,13 +34,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsPair, 1)
 maxsim_umma_pair_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constant__ CUtensorMap tmap_q,
                         const int32_t* __restrict__ chunk_page, const int32_t* __restrict__ unit_start,
                         const int32_t* __restrict__ unit_end, int slot_mode, int n_units, int m_tile_base,
-                        int n_groups_real, typename Kind<KIND>::Acc* __restrict__ group_scores, int64_t ld,
-                        int num_stages) {
+                        int n_groups_real, const uint32_t* __restrict__ clamp_bits,
+                        typename Kind<KIND>::Acc* __restrict__ group_scores, int64_t ld, int num_stages) {
   using K = Kind<KIND>;
   using Acc = typename K::Acc;
   static_assert(NM % 2 == 0, "pair form: an even number of query tiles per CTA (tile m uses accumulator m & 1)");
   constexpr int MPW = NM / 2;  // query tiles per epilogue warpgroup
-  constexpr int kKSteps = KIND == 0 ? 8 : 4;
+  constexpr int kKSteps = K::kKSteps;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -223,8 +223,9 @@ maxsim_umma_pair_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
               if (pg[j] < 0) continue;
               if (pg[j] != cur_page[i]) {
                 if (cur_page[i] >= 0) {
-                  const Acc s2 = warp_sum(runmax[i]);
-                  if (lane == 0) group_scores[int64_t(group) * ld + (slot_mode ? u : cur_page[i])] = s2;
+                  const int o = slot_mode ? u : cur_page[i];
+                  const Acc s2 = warp_sum(clamp_token_max(clamp_bits, o, runmax[i]));
+                  if (lane == 0) group_scores[int64_t(group) * ld + o] = s2;
                 }
                 cur_page[i] = pg[j];
                 runmax[i] = cm[j];
@@ -243,8 +244,9 @@ maxsim_umma_pair_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __g
       for (int i = 0; i < MPW; ++i) {
         const int group = (m_tile_base + int(rank) * NM + buf + 2 * i) * 4 + quad;
         if (group < n_groups_real && cur_page[i] >= 0) {
-          const Acc s2 = warp_sum(runmax[i]);
-          if (lane == 0) group_scores[int64_t(group) * ld + (slot_mode ? u : cur_page[i])] = s2;
+          const int o = slot_mode ? u : cur_page[i];
+          const Acc s2 = warp_sum(clamp_token_max(clamp_bits, o, runmax[i]));
+          if (lane == 0) group_scores[int64_t(group) * ld + o] = s2;
         }
       }
     }
@@ -305,11 +307,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsPair, 1)
 maxsim_umma_pair1_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constant__ CUtensorMap tmap_q,
                          const int32_t* __restrict__ chunk_page, const int32_t* __restrict__ unit_start,
                          const int32_t* __restrict__ unit_end, int slot_mode, int n_units, int m_tile_base,
-                         int n_groups_real, typename Kind<KIND>::Acc* __restrict__ group_scores, int64_t ld,
-                         int num_stages) {
+                         int n_groups_real, const uint32_t* __restrict__ clamp_bits,
+                         typename Kind<KIND>::Acc* __restrict__ group_scores, int64_t ld, int num_stages) {
   using K = Kind<KIND>;
   using Acc = typename K::Acc;
-  constexpr int kKSteps = KIND == 0 ? 8 : 4;
+  constexpr int kKSteps = K::kKSteps;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -458,8 +460,9 @@ maxsim_umma_pair1_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __
       if (group < n_groups_real && w.valid(n_units)) {
         if (w.u != last_u) {  // a new unit starts: units are whole pages
           if (cur_page >= 0) {
-            const Acc s2 = warp_sum(runmax);
-            if (lane == 0) group_scores[int64_t(group) * ld + (slot_mode ? last_u : cur_page)] = s2;
+            const int o = slot_mode ? last_u : cur_page;
+            const Acc s2 = warp_sum(clamp_token_max(clamp_bits, o, runmax));
+            if (lane == 0) group_scores[int64_t(group) * ld + o] = s2;
           }
           cur_page = -1;
           last_u = w.u;
@@ -488,8 +491,9 @@ maxsim_umma_pair1_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __
           if (pg[j] < 0) continue;
           if (pg[j] != cur_page) {
             if (cur_page >= 0) {
-              const Acc s2 = warp_sum(runmax);
-              if (lane == 0) group_scores[int64_t(group) * ld + (slot_mode ? last_u : cur_page)] = s2;
+              const int o = slot_mode ? last_u : cur_page;
+              const Acc s2 = warp_sum(clamp_token_max(clamp_bits, o, runmax));
+              if (lane == 0) group_scores[int64_t(group) * ld + o] = s2;
             }
             cur_page = pg[j];
             runmax = cm[j];
@@ -505,8 +509,9 @@ maxsim_umma_pair1_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __
       }
     }
     if (group < n_groups_real && cur_page >= 0) {
-      const Acc s2 = warp_sum(runmax);
-      if (lane == 0) group_scores[int64_t(group) * ld + (slot_mode ? last_u : cur_page)] = s2;
+      const int o = slot_mode ? last_u : cur_page;
+      const Acc s2 = warp_sum(clamp_token_max(clamp_bits, o, runmax));
+      if (lane == 0) group_scores[int64_t(group) * ld + o] = s2;
     }
   }
 
@@ -550,7 +555,7 @@ static int launch_pair(b200ms_t* h, const UnitPlan& up, const CUtensorMap& tq, i
   if (grid > want) grid = want;
   if (grid < 2) grid = 2;
   kern<<<grid, kThreadsPair, smem, s>>>(c.tmap, tq, static_cast<const int32_t*>(h->chunk_page.p), up.start, up.end,
-                                       up.slot_mode, up.n_units, m_tile_base, n_groups_real,
+                                       up.slot_mode, up.n_units, m_tile_base, n_groups_real, up.clamp_bits,
                                        static_cast<typename K::Acc*>(scores), ld, stages);
   h->launches++;
   return check_cuda(h, cudaGetLastError(), "launch maxsim_umma_pair");
@@ -586,31 +591,35 @@ static int launch_pair1(b200ms_t* h, const UnitPlan& up, const CUtensorMap& tq, 
   if (grid > want) grid = want;
   if (grid < 2) grid = 2;
   kern<<<grid, kThreadsPair, smem, s>>>(c.tmap, tq, static_cast<const int32_t*>(h->chunk_page.p), up.start, up.end,
-                                       up.slot_mode, up.n_units, m_tile_base, n_groups_real,
+                                       up.slot_mode, up.n_units, m_tile_base, n_groups_real, up.clamp_bits,
                                        static_cast<typename K::Acc*>(scores), ld, stages);
   h->launches++;
   return check_cuda(h, cudaGetLastError(), "launch maxsim_umma_pair1");
 }
 
-// nm = query tiles per CTA (1, 2, 4; 8 for int8): one launch scores 2*nm query tiles [m_tile_base, m_tile_base + 2*nm).
-int launch_score_umma_pair(b200ms_t* h, const UnitPlan& up, const CUtensorMap& tq, int nm, int m_tile_base,
-                           int n_groups_real, void* scores, int64_t ld, cudaStream_t s) {
-  const bool bf16 = h->corpus.dtype == B200MS_BF16;
+// nm = query tiles per CTA (1, 2, 4; 8 for the one-byte dtypes): one launch scores 2*nm query tiles [m_tile_base, m_tile_base + 2*nm).
+template <int KIND>
+static int launch_pair_kind(b200ms_t* h, const UnitPlan& up, const CUtensorMap& tq, int nm, int m_tile_base,
+                            int n_groups_real, void* scores, int64_t ld, cudaStream_t s) {
   switch (nm) {
-    case 1:
-      return bf16 ? launch_pair1<0>(h, up, tq, m_tile_base, n_groups_real, scores, ld, s)
-                  : launch_pair1<1>(h, up, tq, m_tile_base, n_groups_real, scores, ld, s);
-    case 2:
-      return bf16 ? launch_pair<0, 2>(h, up, tq, m_tile_base, n_groups_real, scores, ld, s)
-                  : launch_pair<1, 2>(h, up, tq, m_tile_base, n_groups_real, scores, ld, s);
-    case 4:
-      return bf16 ? launch_pair<0, 4>(h, up, tq, m_tile_base, n_groups_real, scores, ld, s)
-                  : launch_pair<1, 4>(h, up, tq, m_tile_base, n_groups_real, scores, ld, s);
+    case 1: return launch_pair1<KIND>(h, up, tq, m_tile_base, n_groups_real, scores, ld, s);
+    case 2: return launch_pair<KIND, 2>(h, up, tq, m_tile_base, n_groups_real, scores, ld, s);
+    case 4: return launch_pair<KIND, 4>(h, up, tq, m_tile_base, n_groups_real, scores, ld, s);
     case 8:
-      if (!bf16) return launch_pair<1, 8>(h, up, tq, m_tile_base, n_groups_real, scores, ld, s);
+      if constexpr (Kind<KIND>::kMaxNM >= 8) return launch_pair<KIND, 8>(h, up, tq, m_tile_base, n_groups_real, scores, ld, s);
       [[fallthrough]];
     default:
       return set_error(h, B200MS_EINVAL, "maxsim_umma_pair: bad NM");
+  }
+}
+
+int launch_score_umma_pair(b200ms_t* h, const UnitPlan& up, const CUtensorMap& tq, int nm, int m_tile_base,
+                           int n_groups_real, void* scores, int64_t ld, cudaStream_t s) {
+  switch (kind_of_dtype(h->corpus.dtype)) {
+    case 0: return launch_pair_kind<0>(h, up, tq, nm, m_tile_base, n_groups_real, scores, ld, s);
+    case 1: return launch_pair_kind<1>(h, up, tq, nm, m_tile_base, n_groups_real, scores, ld, s);
+    case 2: return launch_pair_kind<2>(h, up, tq, nm, m_tile_base, n_groups_real, scores, ld, s);
+    default: return set_error(h, B200MS_ESTATE, "maxsim_umma_pair: corpus dtype has no tcgen05 scorer");
   }
 }
 

@@ -8,6 +8,7 @@
 // One warp converts one destination row (lane l owns elements 4l..4l+3); HBM traffic is one coalesced read of the
 // source row and one coalesced write of the destination row -- these kernels are copy-bound.
 #include <cuda_bf16.h>
+#include <cuda_fp8.h>
 
 #include "common.cuh"
 #include "ptx.cuh"
@@ -43,6 +44,12 @@ __device__ __forceinline__ void store_row4(void* dst, int dst_dtype, int64_t row
   } else if (dst_dtype == B200MS_I8) {
     const uint32_t b0 = uint32_t(quant_i8(v.x, i8_scale)) & 0xffu, b1 = uint32_t(quant_i8(v.y, i8_scale)) & 0xffu;
     const uint32_t b2 = uint32_t(quant_i8(v.z, i8_scale)) & 0xffu, b3 = uint32_t(quant_i8(v.w, i8_scale)) & 0xffu;
+    reinterpret_cast<uint32_t*>(dst)[row * 32 + lane] = b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);
+  } else if (dst_dtype == B200MS_F8) {  // e4m3, round-to-nearest-even, saturating at +-448 (NaN stays NaN)
+    const uint32_t b0 = __nv_cvt_float_to_fp8(v.x * i8_scale, __NV_SATFINITE, __NV_E4M3);
+    const uint32_t b1 = __nv_cvt_float_to_fp8(v.y * i8_scale, __NV_SATFINITE, __NV_E4M3);
+    const uint32_t b2 = __nv_cvt_float_to_fp8(v.z * i8_scale, __NV_SATFINITE, __NV_E4M3);
+    const uint32_t b3 = __nv_cvt_float_to_fp8(v.w * i8_scale, __NV_SATFINITE, __NV_E4M3);
     reinterpret_cast<uint32_t*>(dst)[row * 32 + lane] = b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);
   } else {  // B200MS_B1: element e -> byte e/8, bit 7 - e%8 (MSB first); strict > 0 (0.0, -0.0, NaN -> 0)
     const uint32_t nib = (uint32_t(v.x > 0.f) << 3) | (uint32_t(v.y > 0.f) << 2) | (uint32_t(v.z > 0.f) << 1) |
@@ -114,6 +121,68 @@ __global__ void cand_units_kernel(const int64_t* __restrict__ cand_ids, int n_ca
     const uint32_t bal = __ballot_sync(0xffffffffu, ok);
     if ((threadIdx.x & 31) == 0 && j < n_cand) slot_mask[j >> 5] = bal;
   }
+}
+
+// zero_pad_compat for candidate lists: n_lists lists of n_cand slots (list l at slots [l*stride, l*stride + n_cand)) are
+// "batched" `batch` slots at a time in first-stage order, exactly as score_multi_vector batches the candidate pages
+// (fast_multivector_store.py:553-555, batch_size 128); bit = page shorter than the longest page of its batch.
+// One block per list; the list's page lengths are staged in shared memory (n_cand <= 4096 = B200MS_MAX_K).
+constexpr int kClampMaxCand = 4096;
+__global__ void __launch_bounds__(256)
+clamp_slots_kernel(const int64_t* __restrict__ cand_ids, int n_cand, int64_t stride, int batch,
+                   const int32_t* __restrict__ page_len, int64_t n_pages, uint32_t* __restrict__ clamp_bits) {
+  __shared__ int32_t s_len[kClampMaxCand];
+  __shared__ int32_t s_max[kClampMaxCand];
+  const int64_t base = int64_t(blockIdx.x) * stride;  // a multiple of 32 (0 for a single list)
+  for (int i = threadIdx.x; i < n_cand; i += blockDim.x) {
+    const int64_t id = cand_ids[base + i];
+    s_len[i] = (id >= 0 && id < n_pages) ? __ldg(page_len + id) : 0;
+  }
+  __syncthreads();
+  const int nb = (n_cand + batch - 1) / batch;
+  for (int b = threadIdx.x; b < nb; b += blockDim.x) {
+    int mx = 0;
+    const int e = (b + 1) * batch < n_cand ? (b + 1) * batch : n_cand;
+    for (int i = b * batch; i < e; ++i) mx = max(mx, s_len[i]);
+    s_max[b] = mx;
+  }
+  __syncthreads();
+  for (int w = threadIdx.x; w < (n_cand + 31) / 32; w += blockDim.x) {
+    uint32_t bits = 0;
+    for (int j = 0; j < 32 && w * 32 + j < n_cand; ++j) {
+      const int i = w * 32 + j;
+      if (s_len[i] < s_max[i / batch]) bits |= 1u << j;
+    }
+    clamp_bits[base / 32 + w] = bits;
+  }
+}
+
+int launch_clamp_slots(b200ms_t* h, const int64_t* cand_ids, int n_cand, int n_lists, int64_t list_stride, int batch,
+                       uint32_t* clamp_bits, cudaStream_t s) {
+  if (n_cand <= 0 || n_lists <= 0) return B200MS_OK;
+  if (n_cand > kClampMaxCand)
+    return set_error(h, B200MS_EINVAL, "zero_pad_compat: at most 4096 candidates per list (the reference reranks <= 75)");
+  if (batch < 1) batch = 1;
+  clamp_slots_kernel<<<n_lists, 256, 0, s>>>(cand_ids, n_cand, list_stride, batch, static_cast<const int32_t*>(h->page_len.p),
+                                            h->corpus.n_pages, clamp_bits);
+  h->launches++;
+  return check_cuda(h, cudaGetLastError(), "launch clamp_slots");
+}
+
+// [n_lists, n_cand] -> [n_lists, stride] (stride = roundup(n_cand, 32)), tail slots = -1
+__global__ void pad_cands_kernel(const int64_t* __restrict__ src, int n_cand, int64_t stride, int64_t total, int64_t* __restrict__ dst) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int64_t l = i / stride, j = i % stride;
+  dst[i] = j < n_cand ? src[l * n_cand + j] : int64_t(-1);
+}
+
+int launch_pad_cands(b200ms_t* h, const int64_t* src, int n_cand, int n_lists, int64_t stride, int64_t* dst, cudaStream_t s) {
+  const int64_t total = stride * n_lists;
+  if (total <= 0) return B200MS_OK;
+  pad_cands_kernel<<<unsigned((total + 255) / 256), 256, 0, s>>>(src, n_cand, stride, total, dst);
+  h->launches++;
+  return check_cuda(h, cudaGetLastError(), "launch pad_cands");
 }
 
 int launch_cand_units(b200ms_t* h, const int64_t* cand_ids, int n_cand, int32_t* unit_start, int32_t* unit_end,

@@ -5,6 +5,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <cstdio>
 
 namespace bms {
 
@@ -50,8 +51,20 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// mbarrier.try_wait already suspends the thread for a hardware-bounded time per attempt; after a burst of failed attempts
+// back off with __nanosleep so that a long wait (a peer CTA's tail, a starved producer) stops stealing issue slots from the
+// warps that do the work.  -DB200MS_MBAR_TIMEOUT=<polls> turns a hang into a trap with the barrier address (debug builds).
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t polls = 0;
   while (!mbar_try_wait(bar, parity)) {
+    if (++polls > 32u) __nanosleep(polls > 1024u ? 256u : 32u);
+#ifdef B200MS_MBAR_TIMEOUT
+    if (polls > uint32_t(B200MS_MBAR_TIMEOUT)) {
+      printf("b200ms: mbarrier wait timed out (block %d thread %d bar %p parity %u)\n", int(blockIdx.x), int(threadIdx.x),
+             static_cast<void*>(bar), parity);
+      __trap();
+    }
+#endif
   }
 }
 
@@ -96,7 +109,7 @@ __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence:
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
 // D[tmem] (+)= A[smem] * B[smem]^T ; one thread issues on behalf of the CTA.
-template <int KIND>  // 0: kind::f16 (bf16 in, f32 acc)   1: kind::i8 (s8 in, s32 acc)
+template <int KIND>  // 0: kind::f16 (bf16 in, f32 acc)   1: kind::i8 (s8 in, s32 acc)   2: kind::f8f6f4 (e4m3 in, f32 acc)
 __device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                         uint32_t accumulate) {
   if constexpr (KIND == 0) {
@@ -105,29 +118,17 @@ __device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t a_desc, uint64
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
         "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
+  } else if constexpr (KIND == 2) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
   } else {
     asm volatile(
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
         "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-        : "memory");
-  }
-}
-// Same with the A operand read from TMEM (lane = row, K packed along 32-bit columns).
-template <int KIND>
-__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
-                                        uint32_t accumulate) {
-  if constexpr (KIND == 0) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
-        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
-        : "memory");
-  } else {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
-        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
   }
 }
@@ -188,6 +189,12 @@ __device__ __forceinline__ void umma2_ss(uint32_t d_tmem, uint64_t a_desc, uint6
         "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
         "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
+  } else if constexpr (KIND == 2) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
   } else {
     asm volatile(
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
@@ -219,19 +226,6 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32])
       : "r"(taddr)
       : "memory");
 }
-// registers -> TMEM: this warp's 32 lanes x 32 consecutive 32-bit columns.  Whole warp; tmem_st_wait() before signalling.
-__device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&v)[32]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
-      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
-      "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]),
-      "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]),
-      "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
-      : "memory");
-}
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---------------------------------------------------------------- UMMA descriptors
@@ -247,8 +241,10 @@ __device__ __forceinline__ uint64_t umma_desc_kmajor_sw128(uint32_t smem_addr) {
 // Instruction descriptor (32 bit): c_format [4,6), a_format [7,10), b_format [10,13), a/b major [15],[16] = 0 (K),
 // N>>3 at [17,23), M>>4 at [24,29).
 __host__ __device__ constexpr uint32_t umma_idesc(int kind, int m, int n) {
-  // kind 0: bf16 x bf16 -> f32 (c_format 1, a/b format 1 = BF16); kind 1: s8 x s8 -> s32 (c_format 2, a/b format 1 = INT8)
-  return (uint32_t(kind == 0 ? 1 : 2) << 4) | (1u << 7) | (1u << 10) | (uint32_t(n >> 3) << 17) | (uint32_t(m >> 4) << 24);
+  // kind 0: bf16 x bf16 -> f32 (c_format 1, a/b format 1 = BF16); kind 1: s8 x s8 -> s32 (c_format 2, a/b format 1 = INT8);
+  // kind 2: e4m3 x e4m3 -> f32 (kind::f8f6f4: c_format 1, a/b format 0 = E4M3)
+  return (uint32_t(kind == 1 ? 2 : 1) << 4) | (uint32_t(kind == 2 ? 0 : 1) << 7) | (uint32_t(kind == 2 ? 0 : 1) << 10) |
+         (uint32_t(n >> 3) << 17) | (uint32_t(m >> 4) << 24);
 }
 
 // ---------------------------------------------------------------- small math helpers

@@ -66,7 +66,7 @@ topk_kernel(const T* __restrict__ gs, int64_t n_pages, int64_t ld, const int32_t
             const uint32_t* __restrict__ allow_base, int k, float scale, int64_t id_base, const int64_t* __restrict__ id_map,
             float* __restrict__ top_scores, int64_t* __restrict__ top_ids, int32_t* __restrict__ top_counts,
             int64_t slice_pages, uint32_t* __restrict__ part_keys, int64_t* __restrict__ part_ids,
-            const int32_t* __restrict__ mask_index, int64_t mask_stride) {
+            const int32_t* __restrict__ mask_index, int64_t mask_stride, int64_t q_stride) {
   // grid = (n_q, n_slices): CTA (q, s) selects the exact top-k of pages [s*slice_pages, (s+1)*slice_pages).  With one slice
   // it writes the final result; otherwise (raw key, id) candidates for topk_merge_kernel (global top-k is a subset of the
   // union of the slices' top-k, and both levels order by (key DESC, id ASC), so the result is identical).
@@ -84,8 +84,10 @@ topk_kernel(const T* __restrict__ gs, int64_t n_pages, int64_t ld, const int32_t
   }
   const int g0 = group_offsets[q], g1 = group_offsets[q + 1];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int64_t pbeg = int64_t(blockIdx.y) * slice_pages;
-  const int64_t pend = pbeg + slice_pages < n_pages ? pbeg + slice_pages : n_pages;
+  // q_stride > 0 (batched rerank): query q ranks only its own slots [q*q_stride, q*q_stride + n_pages)
+  const int64_t qbase = int64_t(q) * q_stride;
+  const int64_t pbeg = qbase + int64_t(blockIdx.y) * slice_pages;
+  const int64_t pend = (int64_t(blockIdx.y) + 1) * slice_pages < n_pages ? pbeg + slice_pages : qbase + n_pages;
 
   // ---- radix select of the k-th largest key (4 x 8 bits, most significant first)
   uint32_t prefix = 0, need = 0, total = 0;
@@ -212,11 +214,15 @@ __device__ __forceinline__ bool cand_before(uint32_t ka, int64_t ia, uint32_t kb
 
 // cand_keys != NULL: candidates carry raw order-preserving keys of score type T (second level of topk_kernel; exact for int
 // scores beyond 2^24 too); else float scores (merge of per-shard lists after the all-gather).
+// gathered != NULL: candidates come straight from the all-gather buffer -- `world` blocks (one per rank) of
+// [n_q*kx int64 ids | n_q*kx f32 scores] (the exchange layout the local top-k is written in, include/b200ms.h); candidate
+// i of query q is entry q*kx + i%kx of rank i/kx.  No repacking kernels between the collective and the merge.
 template <typename T>
 __global__ void __launch_bounds__(1024)
 merge_topk_kernel(const float* __restrict__ cand_scores, const uint32_t* __restrict__ cand_keys,
                   const int64_t* __restrict__ cand_ids, int m, int n2, int k, float scale, float* __restrict__ top_scores,
-                  int64_t* __restrict__ top_ids, int32_t* __restrict__ top_counts) {
+                  int64_t* __restrict__ top_ids, int32_t* __restrict__ top_counts, const uint8_t* __restrict__ gathered,
+                  int kx, int64_t rank_stride, int64_t scores_off) {
   extern __shared__ uint8_t msm[];
   int64_t* ids = reinterpret_cast<int64_t*>(msm);
   uint32_t* keys = reinterpret_cast<uint32_t*>(ids + n2);
@@ -229,8 +235,15 @@ merge_topk_kernel(const float* __restrict__ cand_scores, const uint32_t* __restr
     int64_t id = -1;
     uint32_t kraw = 0;
     if (i < m) {
-      id = cand_ids[int64_t(q) * m + i];
-      kraw = cand_keys ? cand_keys[int64_t(q) * m + i] : key_of(cand_scores[int64_t(q) * m + i]);
+      if (gathered) {
+        const uint8_t* blk = gathered + int64_t(i / kx) * rank_stride;
+        const int64_t e = int64_t(q) * kx + (i % kx);
+        id = reinterpret_cast<const int64_t*>(blk)[e];
+        kraw = key_of(reinterpret_cast<const float*>(blk + scores_off)[e]);
+      } else {
+        id = cand_ids[int64_t(q) * m + i];
+        kraw = cand_keys ? cand_keys[int64_t(q) * m + i] : key_of(cand_scores[int64_t(q) * m + i]);
+      }
     }
     const bool ok = id >= 0;
     keys[i] = ok ? kraw : 0u;
@@ -270,7 +283,8 @@ merge_topk_kernel(const float* __restrict__ cand_scores, const uint32_t* __restr
 template <typename T>
 static int launch_merge_impl(b200ms_t* h, const float* cand_scores, const uint32_t* cand_keys, const int64_t* cand_ids, int n_q,
                              int m, int k, float scale, float* top_scores, int64_t* top_ids, int32_t* top_counts,
-                             cudaStream_t s) {
+                             cudaStream_t s, const uint8_t* gathered = nullptr, int kx = 1, int64_t rank_stride = 0,
+                             int64_t scores_off = 0) {
   int n2 = 2;
   while (n2 < m) n2 <<= 1;
   const size_t smem = size_t(n2) * (sizeof(int64_t) + sizeof(uint32_t));
@@ -278,7 +292,8 @@ static int launch_merge_impl(b200ms_t* h, const float* cand_scores, const uint32
   if (int e = check_cuda(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)),
                          "cudaFuncSetAttribute(merge_topk)"))
     return e;
-  kern<<<n_q, 1024, smem, s>>>(cand_scores, cand_keys, cand_ids, m, n2, k, scale, top_scores, top_ids, top_counts);
+  kern<<<n_q, 1024, smem, s>>>(cand_scores, cand_keys, cand_ids, m, n2, k, scale, top_scores, top_ids, top_counts, gathered, kx,
+                               rank_stride, scores_off);
   h->launches++;
   return check_cuda(h, cudaGetLastError(), "launch merge_topk");
 }
@@ -286,7 +301,7 @@ static int launch_merge_impl(b200ms_t* h, const float* cand_scores, const uint32
 int launch_topk(b200ms_t* h, const void* group_scores, int score_dtype, int64_t n_pages, int64_t ld,
                 const int32_t* group_offsets_dev, int n_q, const uint32_t* allow_mask, int k, float scale,
                 int64_t id_base, const int64_t* id_map, float* top_scores, int64_t* top_ids, int32_t* top_counts,
-                cudaStream_t s, const int32_t* mask_index, int64_t mask_stride) {
+                cudaStream_t s, const int32_t* mask_index, int64_t mask_stride, int64_t q_stride) {
   if (n_q <= 0) return B200MS_OK;
   int n2 = 1;
   while (n2 < k) n2 <<= 1;
@@ -312,11 +327,11 @@ int launch_topk(b200ms_t* h, const void* group_scores, int score_dtype, int64_t 
     topk_kernel<float><<<grid, kTopkThreads, smem, s>>>(static_cast<const float*>(group_scores), n_pages, ld,
                                                        group_offsets_dev, allow_mask, k, scale, id_base, id_map, top_scores,
                                                        top_ids, top_counts, slice_pages, part_keys, part_ids, mask_index,
-                                                       mask_stride);
+                                                       mask_stride, q_stride);
   } else {
     topk_kernel<int><<<grid, kTopkThreads, smem, s>>>(static_cast<const int*>(group_scores), n_pages, ld, group_offsets_dev,
                                                      allow_mask, k, scale, id_base, id_map, top_scores, top_ids, top_counts,
-                                                     slice_pages, part_keys, part_ids, mask_index, mask_stride);
+                                                     slice_pages, part_keys, part_ids, mask_index, mask_stride, q_stride);
   }
   h->launches++;
   if (int e = check_cuda(h, cudaGetLastError(), "launch topk")) return e;
@@ -331,6 +346,14 @@ int launch_merge_topk(b200ms_t* h, const float* cand_scores, const int64_t* cand
                       float* top_scores, int64_t* top_ids, int32_t* top_counts, cudaStream_t s) {
   if (n_q <= 0) return B200MS_OK;
   return launch_merge_impl<float>(h, cand_scores, nullptr, cand_ids, n_q, m, k, 1.0f, top_scores, top_ids, top_counts, s);
+}
+
+int launch_merge_gathered(b200ms_t* h, const void* gathered, int world, int n_q, int k, float* top_scores, int64_t* top_ids,
+                          int32_t* top_counts, cudaStream_t s) {
+  if (n_q <= 0) return B200MS_OK;
+  const int64_t n = int64_t(n_q) * k;
+  return launch_merge_impl<float>(h, nullptr, nullptr, nullptr, n_q, world * k, k, 1.0f, top_scores, top_ids, top_counts, s,
+                                  static_cast<const uint8_t*>(gathered), k, n * 12, n * 8);
 }
 
 }  // namespace bms

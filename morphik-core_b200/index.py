@@ -43,14 +43,16 @@ class MaxSimIndex:
 
     def __init__(self, device: int = 0, dtype: str = "bf16", i8_scale: float = 127.0, capacity_rows: int = 0):
         if dtype not in nat.DTYPE_NAMES or nat.DTYPE_NAMES[dtype] == nat.F32:
-            raise ValueError(f"dtype must be one of bf16/int8/binary, got {dtype!r}")
+            raise ValueError(f"dtype must be one of bf16/int8/fp8/binary, got {dtype!r}")
         if not torch.cuda.is_available():
             raise nat.NativeError("MaxSimIndex needs a CUDA device (B200); there is no CPU fallback")
         self.device = torch.device("cuda", int(device))
         self.dtype = nat.DTYPE_NAMES[dtype]
         self.dtype_name = dtype
         self.row_bytes = nat.ROW_BYTES[self.dtype]
-        self.i8_scale = float(i8_scale)  # corpus AND query quantisation scale for int8 (unit-norm rows -> 127)
+        # corpus AND query quantisation scale: int8 rint(x*127) for unit-norm rows; fp8 e4m3(x*64) -- a power of two keeps the
+        # scaling exact and puts |x| in [2^-12, 7] into e4m3's normal range
+        self.i8_scale = 64.0 if (self.dtype == nat.F8 and float(i8_scale) == 127.0) else float(i8_scale)
         self.h = nat.Handle(int(device))
         self._buf: Optional[torch.Tensor] = None  # aligned uint8 storage of the packed rows
         self._cap_rows = 0
@@ -78,9 +80,14 @@ class MaxSimIndex:
         """Factor that turns the kernels' raw sums into reference-scale scores."""
         if self.dtype == nat.B1:
             return 1.0 / 128.0  # sum_t max_r (128 - ham) / 128  == SQL max_sim
-        if self.dtype == nat.I8:
+        if self.dtype in (nat.I8, nat.F8):
             return 1.0 / (self.i8_scale * self.i8_scale)
         return 1.0
+
+    @property
+    def float_scores(self) -> bool:
+        """True when the kernels emit float32 group scores (bf16 / fp8 corpora), False for exact int32 (int8 / binary)."""
+        return self.dtype in (nat.BF16, nat.F8)
 
     def launch_count(self) -> int:
         return int(nat.lib.b200ms_launch_count(self.h.ptr))
@@ -198,6 +205,28 @@ class MaxSimIndex:
         self._page_lens = lens
         self._attached = False
 
+    def append_packed(self, rows: torch.Tensor, page_lens: Sequence[int]) -> Tuple[int, int]:
+        """Append already packed rows (uint8 view of the corpus dtype's layout, pages padded to 32 rows) -- a shard-file
+        segment -- with one device copy.  Returns (first id, count)."""
+        lens = [int(x) for x in page_lens]
+        flat = rows.view(torch.uint8).reshape(-1)
+        need = int(nat.lib.b200ms_padded_rows(nat.i32_array(lens), len(lens)))
+        if flat.numel() < need * self.row_bytes:
+            raise ValueError("packed buffer smaller than the page lengths imply")
+        first = self.n_pages
+        self._grow(self._rows + need)
+        self._buf[self._rows * self.row_bytes:(self._rows + need) * self.row_bytes].copy_(flat[: need * self.row_bytes])
+        self._rows += need
+        self._page_lens.extend(lens)
+        self._attached = False
+        return first, len(lens)
+
+    def page_row_range(self, first: int, n: int) -> Tuple[int, int]:
+        """Padded row range [r0, r1) that pages [first, first+n) occupy in the packed buffer."""
+        pad = [(x + 31) // 32 * 32 for x in self._page_lens]
+        r0 = int(sum(pad[:first]))
+        return r0, r0 + int(sum(pad[first:first + n]))
+
     def _attach(self):
         if self._attached:
             return
@@ -260,6 +289,14 @@ class MaxSimIndex:
         bits = np.concatenate([allowed, np.zeros(pad, dtype=bool)]) if pad else allowed
         return np.packbits(bits.reshape(-1, 32), axis=1, bitorder="little").view(np.uint32).reshape(-1).copy()
 
+    def _check_mask(self, allow_mask) -> np.ndarray:
+        """The library reads ceil(n_pages/32) words: a mask built for an older (shorter) corpus must never reach it."""
+        m = np.ascontiguousarray(allow_mask, dtype=np.uint32)
+        words = (self.n_pages + 31) // 32
+        if m.shape != (words,):
+            raise ValueError(f"allow-mask must have {words} uint32 words for {self.n_pages} pages, got shape {m.shape}")
+        return m
+
     def search_host(self, queries: Sequence[np.ndarray], k: int, allow_mask: Optional[np.ndarray] = None,
                     id_base: int = 0, out: Optional[Tuple[np.ndarray, np.ndarray, np.ndarray]] = None):
         """End-to-end query step from HOST buffers (float32 [T_i,128] each): H2D, pack, scan, top-k, D2H; synchronous.
@@ -279,7 +316,7 @@ class MaxSimIndex:
         ts, ti, tc = out
         mask_p = None
         if allow_mask is not None:
-            allow_mask = np.ascontiguousarray(allow_mask, dtype=np.uint32)
+            allow_mask = self._check_mask(allow_mask)
             mask_p = allow_mask.ctypes.data_as(ctypes.c_void_p)
         self.h.check(
             nat.lib.b200ms_search_host(self.h.ptr, q_host.ctypes.data_as(ctypes.c_void_p), nat.i32_array(lens), n_q, int(k),
@@ -335,7 +372,7 @@ class MaxSimIndex:
         qp = q_host.data_ptr() if isinstance(q_host, torch.Tensor) else q_host.ctypes.data
         mask_p = None
         if allow_mask is not None:
-            allow_mask = np.ascontiguousarray(allow_mask, dtype=np.uint32)
+            allow_mask = self._check_mask(allow_mask)
             mask_p = allow_mask.ctypes.data_as(ctypes.c_void_p)
         self.h.check(
             nat.lib.b200ms_search_host(self.h.ptr, ctypes.c_void_p(qp), nat.i32_array(q_lens), len(q_lens), int(k), mask_p,
@@ -401,7 +438,7 @@ class MaxSimIndex:
         goff = (ctypes.c_int32 * (n_q + 1))()
         ng = ctypes.c_int(0)
         ld = (self.n_pages + 31) // 32 * 32
-        sdt = torch.float32 if self.dtype == nat.BF16 else torch.int32
+        sdt = torch.float32 if self.float_scores else torch.int32
         scores = torch.zeros((gp, max(ld, 32)), dtype=sdt, device=self.device)
         with torch.cuda.device(self.device):
             self.h.check(
@@ -474,6 +511,110 @@ class MaxSimIndex:
                 "b200ms_merge_topk",
             )
         return ts, ti, tc
+
+    # ------------------------------------------------------------------ candidate rerank (two-stage search)
+    def rerank_batch(self, q_dev: torch.Tensor, q_lens: Sequence[int], cand_ids: torch.Tensor, k: int,
+                     out: Optional[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]] = None):
+        """Exact MaxSim of every query over ITS OWN candidate list: cand_ids int64 [n_q, n_cand] on the device (-1 = unused
+        slot) -> (scores [n_q,k], page ids [n_q,k], counts [n_q]) on the device; one call for the whole batch
+        (b200ms_rerank_batch_device; fast_multivector_store.py:545-557 does this one query at a time on <= 75 pages)."""
+        self._attach()
+        n_q = len(q_lens)
+        if cand_ids.dtype != torch.int64 or cand_ids.ndim != 2 or cand_ids.shape[0] != n_q or not cand_ids.is_contiguous():
+            raise ValueError("cand_ids must be a contiguous int64 [n_q, n_cand] device tensor")
+        n_cand = int(cand_ids.shape[1])
+        kk = int(min(k, n_cand))
+        if out is None:
+            out = (torch.empty((n_q, kk), dtype=torch.float32, device=self.device),
+                   torch.empty((n_q, kk), dtype=torch.int64, device=self.device),
+                   torch.empty((n_q,), dtype=torch.int32, device=self.device))
+        ts, ti, tc = out
+        with torch.cuda.device(self.device):
+            self.h.check(
+                nat.lib.b200ms_rerank_batch_device(self.h.ptr, _vp(q_dev), nat.BF16 if q_dev.dtype == torch.bfloat16 else nat.F32,
+                                                   nat.i32_array(q_lens), n_q, _vp(cand_ids), n_cand, kk,
+                                                   ctypes.c_float(self.i8_scale), ctypes.c_float(self.score_scale), _vp(ts),
+                                                   _vp(ti), _vp(tc), self._stream()),
+                "b200ms_rerank_batch_device")
+        return ts, ti, tc
+
+    # ------------------------------------------------------------------ multi-GPU (document shards, NCCL inside libb200ms)
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        """128-byte NCCL unique id (rank 0 creates it; ship it to every rank by any channel)."""
+        buf = (ctypes.c_uint8 * 128)()
+        rc = nat.lib.b200ms_comm_unique_id(buf)
+        if rc != 0:
+            msg = nat.lib.b200ms_last_error(None)
+            raise nat.NativeError(f"b200ms_comm_unique_id failed ({rc}): {msg.decode() if msg else ''}")
+        return bytes(buf)
+
+    def comm_init(self, unique_id: bytes, rank: int, world: int):
+        """Collective: create this handle's NCCL communicator (libb200ms dlopens libnccl; torch is not involved)."""
+        if len(unique_id) != 128:
+            raise ValueError("unique_id must be the 128 bytes of comm_unique_id()")
+        buf = (ctypes.c_uint8 * 128).from_buffer_copy(unique_id)
+        with torch.cuda.device(self.device):
+            self.h.check(nat.lib.b200ms_comm_init(self.h.ptr, buf, int(rank), int(world)), "b200ms_comm_init")
+
+    def bcast(self, t: torch.Tensor, root: int = 0):
+        """ncclBroadcast of a contiguous device tensor in place (e.g. the query rows of a batch) on torch's current stream."""
+        with torch.cuda.device(self.device):
+            self.h.check(nat.lib.b200ms_bcast_device(self.h.ptr, _vp(t), t.numel() * t.element_size(), int(root), self._stream()),
+                         "b200ms_bcast_device")
+        return t
+
+    def allgather_topk(self, xchg: torch.Tensor, n_q: int, k: int, out=None):
+        """The one collective of the path for a caller-made local list: xchg = uint8 device buffer in the exchange layout
+        ([n_q*k int64 global ids][n_q*k float32 scores]) -> merged (scores, ids, counts), identical on every rank."""
+        if out is None:
+            out = (torch.empty((n_q, k), dtype=torch.float32, device=self.device),
+                   torch.empty((n_q, k), dtype=torch.int64, device=self.device),
+                   torch.empty((n_q,), dtype=torch.int32, device=self.device))
+        ts, ti, tc = out
+        with torch.cuda.device(self.device):
+            self.h.check(nat.lib.b200ms_allgather_topk(self.h.ptr, None, _vp(xchg), int(n_q), int(k), _vp(ts), _vp(ti), _vp(tc),
+                                                       self._stream()), "b200ms_allgather_topk")
+        return ts, ti, tc
+
+    def sharded_search_begin(self, q_dev: torch.Tensor, q_lens: Sequence[int], k: int, id_base: int,
+                             out: Tuple[torch.Tensor, torch.Tensor, torch.Tensor],
+                             allow_masks_dev: Optional[torch.Tensor] = None, mask_index_dev: Optional[torch.Tensor] = None) -> int:
+        """Enqueue local scan + top-k on torch's current stream and the all-gather + merge behind it on the handle's
+        communication stream; returns a ticket.  The current stream does not wait for the other ranks."""
+        self._attach()
+        ts, ti, tc = out
+        n_masks = 0 if allow_masks_dev is None else int(allow_masks_dev.shape[0])
+        with torch.cuda.device(self.device):
+            t = int(nat.lib.b200ms_sharded_search_begin(
+                self.h.ptr, _vp(q_dev), nat.BF16 if q_dev.dtype == torch.bfloat16 else nat.F32, nat.i32_array(q_lens), len(q_lens),
+                int(k), _vp(allow_masks_dev), n_masks, _vp(mask_index_dev), ctypes.c_float(self.i8_scale),
+                ctypes.c_float(self.score_scale), int(id_base), _vp(ts), _vp(ti), _vp(tc), self._stream()))
+        if t < 0:
+            self.h.check(t, "b200ms_sharded_search_begin")
+        return t
+
+    def sharded_search_end(self, ticket: int):
+        """Make torch's current stream wait for that ticket's merged result (in the buffers given to begin)."""
+        with torch.cuda.device(self.device):
+            self.h.check(nat.lib.b200ms_sharded_search_end(self.h.ptr, int(ticket), self._stream()), "b200ms_sharded_search_end")
+
+    def sharded_search_host_begin(self, q_host: torch.Tensor, q_lens: Sequence[int], k: int, id_base: int) -> int:
+        """Host-buffer form: q_host float32 [sum T,128] (pinned for an asynchronous copy); returns a ticket."""
+        self._attach()
+        t = int(nat.lib.b200ms_sharded_search_host_begin(
+            self.h.ptr, ctypes.c_void_p(q_host.data_ptr()), nat.i32_array(q_lens), len(q_lens), int(k), None, 0, None,
+            ctypes.c_float(self.i8_scale), ctypes.c_float(self.score_scale), int(id_base)))
+        if t < 0:
+            self.h.check(t, "b200ms_sharded_search_host_begin")
+        return t
+
+    def sharded_search_host_end(self, ticket: int, out_scores: torch.Tensor, out_ids: torch.Tensor, out_counts: torch.Tensor):
+        """Blocks until the ticket's merged top-k is on the host; fills the three (host) tensors."""
+        self.h.check(nat.lib.b200ms_sharded_search_host_end(self.h.ptr, int(ticket), ctypes.c_void_p(out_scores.data_ptr()),
+                                                            ctypes.c_void_p(out_ids.data_ptr()),
+                                                            ctypes.c_void_p(out_counts.data_ptr())),
+                     "b200ms_sharded_search_host_end")
 
     def close(self):
         self.h.close()

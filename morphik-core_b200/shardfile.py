@@ -17,7 +17,7 @@ from __future__ import annotations
 
 import json
 import os
-from typing import Iterable, List, Sequence, Tuple
+from typing import Iterable, List, Optional, Sequence, Tuple
 
 import numpy as np
 import torch
@@ -34,12 +34,16 @@ def _round_up(x: int, a: int) -> int:
     return (x + a - 1) // a * a
 
 
-def save_index(index: MaxSimIndex, path: str) -> int:
-    """Write the packed corpus of `index` to `path`; returns bytes written."""
-    lens = np.asarray(index.page_lens, dtype=np.int32)
-    rows = index.packed_rows().reshape(-1)  # uint8 device view
+def save_index(index: MaxSimIndex, path: str, first_page: int = 0, n_pages: Optional[int] = None) -> int:
+    """Write the packed corpus of `index` (or only pages [first_page, first_page + n_pages): a journal segment) to `path`;
+    returns bytes written."""
+    all_lens = np.asarray(index.page_lens, dtype=np.int32)
+    n_pages = len(all_lens) - first_page if n_pages is None else int(n_pages)
+    lens = all_lens[first_page:first_page + n_pages]
+    r0, r1 = index.page_row_range(first_page, n_pages)
+    rows = index.packed_rows()[r0:r1].reshape(-1)  # uint8 device view
     header = {"magic": MAGIC, "version": 1, "dtype": index.dtype_name, "n_pages": int(len(lens)),
-              "n_rows_padded": int(index.n_rows_padded), "row_bytes": int(index.row_bytes), "i8_scale": float(index.i8_scale)}
+              "n_rows_padded": int(r1 - r0), "row_bytes": int(index.row_bytes), "i8_scale": float(index.i8_scale)}
     blob = json.dumps(header).encode()
     assert len(blob) < HEADER_BYTES
     lens_bytes = _round_up(lens.nbytes, 4096)
@@ -66,10 +70,13 @@ def read_header(path: str) -> Tuple[dict, np.ndarray, int]:
     return header, lens, payload_off
 
 
-def load_index(path: str, device: int = 0) -> MaxSimIndex:
-    """Read a shard file straight into a 1024-byte-aligned device buffer and adopt it (no repacking)."""
+def load_index(path: str, device: int = 0, into: Optional[MaxSimIndex] = None) -> MaxSimIndex:
+    """Read a shard file straight into a 1024-byte-aligned device buffer and adopt it (no repacking); with ``into`` the
+    pages are APPENDED to an existing index of the same dtype (journal segments)."""
     header, lens, payload_off = read_header(path)
-    index = MaxSimIndex(device=device, dtype=header["dtype"], i8_scale=header["i8_scale"])
+    if into is not None and (into.dtype_name != header["dtype"] or float(into.i8_scale) != float(header["i8_scale"])):
+        raise ValueError(f"{path}: segment dtype/scale differs from the index it is appended to")
+    index = into if into is not None else MaxSimIndex(device=device, dtype=header["dtype"], i8_scale=header["i8_scale"])
     total = header["n_rows_padded"] * header["row_bytes"]
     if int(nat.lib.b200ms_padded_rows(nat.i32_array(lens.tolist()), len(lens))) != header["n_rows_padded"]:
         raise ValueError(f"{path}: page lengths do not match the row count")
@@ -91,8 +98,99 @@ def load_index(path: str, device: int = 0) -> MaxSimIndex:
             buf[o:o + n].copy_(st[:n], non_blocking=True)
             events[i & 1].record()
         torch.cuda.current_stream().synchronize()
-    index.adopt_packed(buf, lens.tolist())
+    if into is not None:
+        index.append_packed(buf, lens.tolist())
+    else:
+        index.adopt_packed(buf, lens.tolist())
     return index
+
+
+class StoreJournal:
+    """Append-only durable form of a store directory (SURVEY 8f-2 "incremental append/delete by document").
+
+    The reference persists every ``store_embeddings`` call as it happens (one ``.npy`` per page,
+    fast_multivector_store.py:673-707; rows in Postgres, multi_vector_store.py:681-703) and deletes by document id
+    (multi_vector_store.py:929-933).  Here the same two operations append to a directory instead of rewriting one file:
+
+        journal.log          one JSON line per operation, in order:
+                               {"op":"segment","seq":N,"pages":P}      pages added by one store_embeddings call
+                               {"op":"delete","document_id":"..."}     tombstone
+        seg-NNNNNN.b2ms      the packed rows of those pages (B2MSHARD v1, exactly the HBM layout)
+        seg-NNNNNN.cat.jsonl their catalogue records (document_id, chunk_number, content, metadata, app_id, n_rows)
+        seg-NNNNNN.fde.pt    (two-stage stores) their FDE rows + inverse norms
+
+    Replaying the log in order reproduces the store; ``checkpoint`` (store.save) rewrites the live pages as one segment and
+    truncates the log.  Every file is written to a temporary name and renamed, the log line is appended (and fsynced) last,
+    so a crash leaves either the old state or the new one.
+    """
+
+    LOG = "journal.log"
+
+    def __init__(self, directory: str):
+        self.dir = directory
+        os.makedirs(directory, exist_ok=True)
+        self.seq = 0
+        for op in self.read_ops():
+            if op.get("op") == "segment":
+                self.seq = max(self.seq, int(op["seq"]))
+
+    def _path(self, name: str) -> str:
+        return os.path.join(self.dir, name)
+
+    def read_ops(self) -> List[dict]:
+        p = self._path(self.LOG)
+        if not os.path.exists(p):
+            return []
+        ops = []
+        with open(p) as f:
+            for line in f:
+                line = line.strip()
+                if not line:
+                    continue
+                try:
+                    ops.append(json.loads(line))
+                except json.JSONDecodeError:  # a torn last line (crash mid-append): everything before it is intact
+                    break
+        return ops
+
+    def _append(self, op: dict) -> None:
+        with open(self._path(self.LOG), "a") as f:
+            f.write(json.dumps(op) + "\n")
+            f.flush()
+            os.fsync(f.fileno())
+
+    def log_add(self, index: MaxSimIndex, first_page: int, n_pages: int, records: Sequence[dict], fde=None) -> int:
+        self.seq += 1
+        stem = f"seg-{self.seq:06d}"
+        tmp = self._path(stem + ".b2ms.tmp")
+        save_index(index, tmp, first_page, n_pages)
+        os.replace(tmp, self._path(stem + ".b2ms"))
+        tmp = self._path(stem + ".cat.jsonl.tmp")
+        with open(tmp, "w") as f:
+            for r in records:
+                f.write(json.dumps(r) + "\n")
+        os.replace(tmp, self._path(stem + ".cat.jsonl"))
+        if fde is not None:
+            rows, inv = fde
+            tmp = self._path(stem + ".fde.pt.tmp")
+            torch.save({"rows": rows.detach().cpu().view(torch.int16), "inv": inv.detach().cpu()}, tmp)
+            os.replace(tmp, self._path(stem + ".fde.pt"))
+        self._append({"op": "segment", "seq": self.seq, "pages": int(n_pages)})
+        return self.seq
+
+    def log_delete(self, document_id: str) -> None:
+        self._append({"op": "delete", "document_id": document_id})
+
+    def segment_files(self, seq: int) -> Tuple[str, str, str]:
+        stem = f"seg-{int(seq):06d}"
+        return self._path(stem + ".b2ms"), self._path(stem + ".cat.jsonl"), self._path(stem + ".fde.pt")
+
+    def reset(self) -> None:
+        """Drop every segment and the log (checkpoint writes a fresh base segment right after)."""
+        for name in os.listdir(self.dir):
+            if name == self.LOG or name.startswith("seg-"):
+                os.remove(self._path(name))
+        self.seq = 0
 
 
 def import_npy_pages(index: MaxSimIndex, paths: Sequence[str], batch: int = 256) -> int:

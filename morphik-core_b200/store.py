@@ -180,7 +180,7 @@ class B200MultiVectorStore(QueryCoalescer, BaseVectorStore):
     def __init__(self, uri: str = "b200://0", device: int = 0, mode: str = "bf16", storage: Any = None,
                  auto_initialize: bool = True, compact_dead_fraction: float = 0.3, index: Any = None,
                  fde_candidates: Optional[int] = None, coalesce_queries: bool = True, max_coalesced_tokens: int = 1024,
-                 max_coalesced_queries: int = 64):
+                 max_coalesced_queries: int = 64, zero_pad_compat: int = 0):
         self.uri = uri
         self.device = int(device)
         self.mode = mode
@@ -192,8 +192,13 @@ class B200MultiVectorStore(QueryCoalescer, BaseVectorStore):
         # the "morphik" provider -- FDE candidates (the reference asks Turbopuffer for min(10*k, 75)) then MaxSim rerank.
         self.fde_candidates = fde_candidates
         self._two_stage = None
+        # > 0: reproduce colpali_engine score_multi_vector's zero-padding quirk with this batch size (128 upstream): a page
+        # shorter than the longest page of its scoring batch scores sum_t max(max_r <q_t,d_r>, 0)  (SURVEY App. A.2;
+        # processing_colpali.py:350-362).  0 (default) = the clean MaxSim.
+        self.zero_pad_compat = int(zero_pad_compat)
         self._init_coalescer(coalesce_queries, max_coalesced_tokens, max_coalesced_queries)  # see module docstring
         self._lock = threading.Lock()
+        self._journal = None  # shardfile.StoreJournal when the store is durable (B200MultiVectorStore.open)
         self._last_store_metrics: Dict[str, Any] = {}
         self.last_query_timing: Dict[str, float] = {}
         if auto_initialize:
@@ -211,6 +216,14 @@ class B200MultiVectorStore(QueryCoalescer, BaseVectorStore):
                 self._index = self._two_stage.index
             else:
                 self._index = MaxSimIndex(device=self.device, dtype=self.mode)
+        elif self.fde_candidates and self._two_stage is None and hasattr(self._index, "h"):
+            # a loaded / injected CUDA index in two-stage mode: rebuild the FDE matrix from its packed rows
+            from .fde import TwoStageIndex
+
+            self._two_stage = TwoStageIndex(index=self._index)
+            self._two_stage.rebuild_from_index()
+        if self.zero_pad_compat and hasattr(self._index, "set_option"):
+            self._index.set_option("zero_pad_compat", self.zero_pad_compat)
         return True
 
     def close(self) -> None:
@@ -247,10 +260,20 @@ class B200MultiVectorStore(QueryCoalescer, BaseVectorStore):
     def _add_pages_locked(self, valid, app_id):
         with self._lock:
             first, n = (self._two_stage or self._index).add_pages([e for _, e in valid])
+            recs = []
             for i, (c, e) in enumerate(valid):
-                pid = self.catalog.add(PageRecord(c.document_id, int(c.chunk_number), c.content, dict(c.metadata or {}),
-                                                  app_id, int(e.shape[0])))
+                rec = PageRecord(c.document_id, int(c.chunk_number), c.content, dict(c.metadata or {}), app_id, int(e.shape[0]))
+                pid = self.catalog.add(rec)
                 assert pid == first + i, "catalogue and device corpus out of step"
+                recs.append(rec)
+            if self._journal is not None:  # durable store: this call becomes one append-only segment
+                fde = self._two_stage.fde_rows(first, n) if self._two_stage is not None else None
+                self._journal.log_add(self._index, first, n, [self._record_json(r) for r in recs], fde)
+
+    @staticmethod
+    def _record_json(r: PageRecord) -> Dict[str, Any]:
+        return {"document_id": r.document_id, "chunk_number": r.chunk_number, "content": r.content, "metadata": r.metadata,
+                "app_id": r.app_id, "n_rows": r.n_rows}
 
     # ------------------------------------------------------------------ read path
     async def query_similar(self, query_embedding, k: int, doc_ids: Optional[List[str]] = None,
@@ -278,6 +301,8 @@ class B200MultiVectorStore(QueryCoalescer, BaseVectorStore):
                     live.append((i, r, words))
             if live:
                 kk = min(max(r.k for _, r, _ in live), n, 4096)
+                if max(r.k for _, r, _ in live) > 4096:
+                    logger.warning("k > 4096 requested; truncated to 4096 (B200MS_MAX_K)")
                 queries = [r.q for _, r, _ in live]
                 masks = [w for _, _, w in live]
                 if self._two_stage is None and hasattr(self._index, "search_host_masked") and len(live) > 1:
@@ -313,22 +338,38 @@ class B200MultiVectorStore(QueryCoalescer, BaseVectorStore):
         """Batched form (extension): one corpus pass scores every query of the batch.
 
         ``min_score`` drops hits scoring below it (the reference accepts ``min_score`` in retrieve_chunks but never applies
-        it, document_service.py:381-383) -- scores are MaxSim sums, so the threshold is on that scale."""
-        t0 = time.perf_counter()
+        it, document_service.py:381-383) -- scores are MaxSim sums, so the threshold is on that scale.
+        Mask construction, the GPU search and the id -> DocumentChunk resolution run in ONE worker-thread call under the
+        store lock, so an ingest or compaction can never slip between them."""
         queries = [as_query_matrix(q) for q in query_embeddings]
-        if len(self.catalog) == 0 or k <= 0:
+        if k <= 0:
             return [[] for _ in queries]
-        visible, words = self.catalog.allow_words(doc_ids, app_id)
-        if not visible:
-            return [[] for _ in queries]
-        kk = min(int(k), len(self.catalog), 4096)
-        t1 = time.perf_counter()
-        ts, ti, tc = await asyncio.to_thread(self._search_locked, queries, kk, words)
-        t2 = time.perf_counter()
-        out = [self._chunks(ts[qi], ti[qi], int(tc[qi]), min_score) for qi in range(len(queries))]
-        t3 = time.perf_counter()
+        return await asyncio.to_thread(self._search_batch_locked, queries, int(k), doc_ids, app_id, min_score)
+
+    def _search_batch_locked(self, queries, k, doc_ids, app_id, min_score):
+        t0 = time.perf_counter()
+        with self._lock:
+            n = len(self.catalog)
+            if n == 0:
+                return [[] for _ in queries]
+            visible, words = self.catalog.allow_words(doc_ids, app_id)
+            if not visible:
+                return [[] for _ in queries]
+            if k > 4096:
+                logger.warning("k=%d requested; truncated to 4096 (B200MS_MAX_K)", k)
+            kk = min(int(k), n, 4096)
+            t1 = time.perf_counter()
+            ts, ti, tc = self._search_unlocked(queries, kk, words)
+            t2 = time.perf_counter()
+            out = [self._chunks(ts[qi], ti[qi], int(tc[qi]), min_score) for qi in range(len(queries))]
+            t3 = time.perf_counter()
         self.last_query_timing = {"prepare_ms": (t1 - t0) * 1e3, "gpu_search_ms": (t2 - t1) * 1e3,
                                   "build_chunks_ms": (t3 - t2) * 1e3, "total_ms": (t3 - t0) * 1e3}
+        if self._two_stage is not None:  # the reference's stage names (fast_multivector_store.py:523,534,550,574,589,604)
+            st = self._two_stage.last_timing_ms
+            self.last_query_timing.update(encode_query_ms=st.get("encode_query_ms", 0.0), ns_query_ms=st.get("ns_query_ms", 0.0),
+                                          load_multivectors_ms=0.0, rerank_scoring_ms=st.get("rerank_scoring_ms", 0.0),
+                                          load_contents_ms=0.0)
         logger.debug("query_similar timing %s", json.dumps(self.last_query_timing))
         return out
 
@@ -358,15 +399,20 @@ class B200MultiVectorStore(QueryCoalescer, BaseVectorStore):
         return out
 
     async def delete_chunks_by_document_id(self, document_id: str, app_id: Optional[str] = None) -> bool:
-        try:
-            with self._lock:
-                self.catalog.delete_document(document_id)
-                if self.catalog.dead_fraction > self.compact_dead_fraction:
-                    self._compact_locked()
+        try:  # off the event loop: the lock may be held by a GPU pass, and a compaction copies device memory
+            await asyncio.to_thread(self._delete_locked, document_id)
             return True
         except Exception as e:  # noqa: BLE001  (reference returns False on error: multi_vector_store.py:949-951)
             logger.error("Error deleting chunks for document %s: %s", document_id, e)
             return False
+
+    def _delete_locked(self, document_id: str) -> None:
+        with self._lock:
+            self.catalog.delete_document(document_id)
+            if self._journal is not None:
+                self._journal.log_delete(document_id)
+            if self.catalog.dead_fraction > self.compact_dead_fraction:
+                self._compact_locked()
 
     def _compact_locked(self):
         """Drop tombstoned pages: rebuild the device corpus from the surviving packed rows (device-to-device)."""
@@ -378,7 +424,9 @@ class B200MultiVectorStore(QueryCoalescer, BaseVectorStore):
 
     # ------------------------------------------------------------------ persistence
     def save(self, directory: str) -> None:
-        """Packed shard file + catalogue (JSON lines).  Tombstoned pages are compacted away first."""
+        """Checkpoint: tombstoned pages are compacted away and the live corpus is written as ONE base segment of a journal
+        directory (shardfile.StoreJournal); the legacy pair corpus.b2ms + catalog.jsonl is written too so that
+        ``load`` of older callers keeps working."""
         import os
 
         from . import shardfile
@@ -390,8 +438,12 @@ class B200MultiVectorStore(QueryCoalescer, BaseVectorStore):
             shardfile.save_index(self._index, os.path.join(directory, "corpus.b2ms"))
             with open(os.path.join(directory, "catalog.jsonl"), "w") as f:
                 for r in self.catalog.records:
-                    f.write(json.dumps({"document_id": r.document_id, "chunk_number": r.chunk_number, "content": r.content,
-                                        "metadata": r.metadata, "app_id": r.app_id, "n_rows": r.n_rows}) + "\n")
+                    f.write(json.dumps(self._record_json(r)) + "\n")
+            if self._journal is not None and os.path.abspath(self._journal.dir) == os.path.abspath(directory):
+                self._journal.reset()
+                if len(self.catalog):
+                    fde = self._two_stage.fde_rows(0, len(self.catalog)) if self._two_stage is not None else None
+                    self._journal.log_add(self._index, 0, len(self.catalog), [self._record_json(r) for r in self.catalog.records], fde)
 
     @classmethod
     def load(cls, directory: str, device: int = 0, **kw) -> "B200MultiVectorStore":
@@ -407,4 +459,43 @@ class B200MultiVectorStore(QueryCoalescer, BaseVectorStore):
                 store.catalog.add(PageRecord(d["document_id"], d["chunk_number"], d["content"], d["metadata"], d["app_id"], d["n_rows"]))
         if len(store.catalog) != index.n_pages:
             raise ValueError("catalogue and shard file disagree on the page count")
+        store.initialize()  # two-stage mode: rebuilds the FDE matrix from the packed rows; applies zero_pad_compat
+        return store
+
+    @classmethod
+    def open(cls, directory: str, device: int = 0, mode: str = "bf16", **kw) -> "B200MultiVectorStore":
+        """Durable store: replay ``directory``'s journal (segments appended by earlier store_embeddings calls, tombstones of
+        earlier deletes -- fast_multivector_store.py:673-707 / multi_vector_store.py:929-933 persist the same two operations)
+        and keep journaling.  Nothing is ever rewritten in place; ``save(directory)`` checkpoints."""
+        import os
+
+        import torch
+
+        from . import shardfile
+
+        journal = shardfile.StoreJournal(directory)
+        store = cls(device=device, mode=mode, **kw)
+        for op in journal.read_ops():
+            if op["op"] == "segment":
+                seg, cat, fde = journal.segment_files(op["seq"])
+                first = store._index.n_pages
+                shardfile.load_index(seg, device=device, into=store._index)
+                with open(cat) as f:
+                    for line in f:
+                        d = json.loads(line)
+                        store.catalog.add(PageRecord(d["document_id"], d["chunk_number"], d["content"], d["metadata"], d["app_id"], d["n_rows"]))
+                if store._two_stage is not None:
+                    if os.path.exists(fde):
+                        blob = torch.load(fde)
+                        store._two_stage.append_fde_rows(blob["rows"].view(torch.bfloat16), blob["inv"])
+                    else:
+                        store._two_stage.rebuild_from_index()
+                if store._index.n_pages - first != int(op["pages"]) or len(store.catalog) != store._index.n_pages:
+                    raise ValueError(f"{seg}: segment and journal disagree on the page count")
+            elif op["op"] == "delete":
+                store.catalog.delete_document(op["document_id"])
+        with store._lock:
+            if store.catalog.dead_fraction > store.compact_dead_fraction:
+                store._compact_locked()
+        store._journal = journal
         return store

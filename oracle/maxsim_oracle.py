@@ -57,6 +57,7 @@ def c_oracle() -> ctypes.CDLL:
         lib.oracle_topk.argtypes = [vp, i64, vp, i64, vp, vp]
         lib.oracle_topk.restype = i64
         lib.oracle_fde_encode.argtypes = [vp, i64, i32, i32, i32, i32, ctypes.c_float, vp, vp, vp, i32, vp]
+        lib.oracle_fde_encode_ex.argtypes = [vp, i64, i32, i32, i32, i32, ctypes.c_float, vp, vp, vp, i32, i32, i32, vp, vp, vp]
         _lib = lib
     return _lib
 
@@ -285,6 +286,57 @@ def fde_encode_c_proj(x, simhash, ams_index, ams_sign, scale, is_document, proj)
     c_oracle().oracle_fde_encode(_ptr(x), x.shape[0], dim, reps, ksim, proj, ctypes.c_float(scale), _ptr(simhash),
                                  _ptr(ams_index), _ptr(ams_sign), int(is_document), _ptr(out))
     return out
+
+
+def fde_encode_c_ex(x, simhash, ams_index, ams_sign, scale, is_document, proj, fill_empty=False, final_index=None,
+                    final_sign=None, final_dim=0) -> np.ndarray:
+    """oracle_fde_encode_ex: + fill_empty_partitions and the final count-sketch projection."""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    simhash = np.ascontiguousarray(simhash, dtype=np.float32)
+    ams_index = np.ascontiguousarray(ams_index, dtype=np.int32)
+    ams_sign = np.ascontiguousarray(ams_sign, dtype=np.float32)
+    reps, dim, ksim = simhash.shape
+    inner = reps * (1 << ksim) * proj
+    out = np.zeros(final_dim if final_dim > 0 else inner, dtype=np.float32)
+    fi = None if final_dim <= 0 else np.ascontiguousarray(final_index, dtype=np.int32)
+    fs = None if final_dim <= 0 else np.ascontiguousarray(final_sign, dtype=np.float32)
+    c_oracle().oracle_fde_encode_ex(_ptr(x), x.shape[0], dim, reps, ksim, proj, ctypes.c_float(scale), _ptr(simhash),
+                                    _ptr(ams_index), _ptr(ams_sign), int(is_document), int(fill_empty), int(final_dim),
+                                    _ptr(fi), _ptr(fs), _ptr(out))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# fp8 e4m3 (B200MS_F8 corpora; new relative to the reference, like int8): round-to-nearest-even onto the 127 finite
+# non-negative e4m3 values, saturating at 448 -- what __nv_cvt_float_to_fp8(x, __NV_SATFINITE, __NV_E4M3) does.
+# ------------------------------------------------------------------------------------------------
+def _e4m3_table() -> np.ndarray:
+    vals = []
+    for code in range(0x7F):  # 0x7f is NaN
+        e, m = code >> 3, code & 7
+        vals.append((m / 8.0) * 2.0 ** -6 if e == 0 else (1.0 + m / 8.0) * 2.0 ** (e - 7))
+    return np.asarray(vals, dtype=np.float64)
+
+
+_E4M3 = _e4m3_table()
+
+
+def quantize_e4m3_np(x: np.ndarray, scale: float = 64.0) -> np.ndarray:
+    """float -> e4m3 CODES (uint8) of x*scale, round-to-nearest-even (ties -> even code), |x*scale| > 448 saturates."""
+    y = np.asarray(x, dtype=np.float32).astype(np.float64) * float(scale)
+    a = np.minimum(np.abs(y), 448.0)
+    hi = np.clip(np.searchsorted(_E4M3, a, side="left"), 0, len(_E4M3) - 1)
+    lo = np.maximum(hi - 1, 0)
+    d_lo, d_hi = a - _E4M3[lo], _E4M3[hi] - a
+    pick_hi = (d_hi < d_lo) | ((d_hi == d_lo) & (hi % 2 == 0))
+    code = np.where(pick_hi, hi, lo).astype(np.uint8)
+    return code | (np.signbit(y).astype(np.uint8) << 7)
+
+
+def dequantize_e4m3_np(codes: np.ndarray) -> np.ndarray:
+    c = np.asarray(codes, dtype=np.uint8)
+    v = _E4M3[(c & 0x7F).astype(np.int64)]
+    return np.where(c & 0x80, -v, v).astype(np.float32)
 
 
 def fde_encode_np(x: np.ndarray, simhash: np.ndarray, ams_index: np.ndarray, ams_sign: np.ndarray, scale: float,

@@ -46,11 +46,11 @@ def test_layout_helpers():
     from morphik_core_b200 import _native as nat
 
     lib = nat.lib
-    assert lib.b200ms_version() == 101
+    assert lib.b200ms_version() == 200
     assert [lib.b200ms_padded_len(n) for n in (0, 1, 31, 32, 33, 1024, 1030)] == [0, 32, 32, 32, 64, 1024, 1056]
     lens = nat.i32_array([0, 1, 32, 33, 1024])
     assert lib.b200ms_padded_rows(lens, 5) == 0 + 32 + 32 + 64 + 1024
-    assert [lib.b200ms_row_bytes(d) for d in (nat.F32, nat.BF16, nat.I8, nat.B1, 99)] == [512, 256, 128, 16, 0]
+    assert [lib.b200ms_row_bytes(d) for d in (nat.F32, nat.BF16, nat.I8, nat.B1, nat.F8, 99)] == [512, 256, 128, 16, 128, 0]
     assert lib.b200ms_query_groups(nat.i32_array([32, 20, 33, 0, 1030]), 5) == 1 + 1 + 2 + 0 + 33
 
 

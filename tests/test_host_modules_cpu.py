@@ -21,7 +21,7 @@ def test_fde_config_mirrors_reference_call_site():
     c = fde.fde_matrices(fde.FixedDimensionalEncodingConfig(seed=2))
     assert not np.array_equal(a[0], c[0])
     assert np.array_equal(a[0][1], c[0][0])  # repetition r of seed s uses stream s + r
-    for bad in (dict(dimension=64), dict(projection_type="DEFAULT_IDENTITY"), dict(fill_empty_partitions=True)):
+    for bad in (dict(dimension=64), dict(projection_type="DEFAULT_IDENTITY"), dict(final_projection_dimension=100)):
         with pytest.raises(ValueError):
             fde.fde_matrices(fde.FixedDimensionalEncodingConfig(**bad))
 

@@ -1,6 +1,7 @@
-"""World-size-2 test of the multi-GPU host logic on CPU (gloo): shard plan, exchange-buffer packing, the single
-all-gather, and the merge order.  Local search and merge are oracle-backed test doubles (the product injects the CUDA
-MaxSimIndex methods instead -- morphik-core_b200/sharded.py:ShardedMaxSim.from_index)."""
+"""World-size-2 test of the multi-GPU host logic on CPU (gloo): shard plan (equal and rate-weighted), the exchange layout
+the local top-k is written into, the single all-gather, and the merge order.  Local search and merge are oracle-backed
+test doubles (the product runs the same layout through libb200ms: b200ms_sharded_search_begin/_end with NCCL --
+morphik-core_b200/sharded.py:ShardedMaxSim.from_index)."""
 import os
 import socket
 
@@ -10,7 +11,8 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from morphik_core_b200.sharded import ShardedMaxSim, pack_exchange, plan_document_shards, unpack_exchange
+from morphik_core_b200.sharded import (ShardedMaxSim, exchange_bytes, exchange_views, gathered_candidates,
+                                       plan_document_shards)
 from oracle import maxsim_oracle as orc
 
 
@@ -29,11 +31,29 @@ def test_plan_document_shards_balanced_and_contiguous():
     assert plan_document_shards([], 2) == [(0, 0), (0, 0)]
 
 
-def test_pack_unpack_exchange_roundtrip():
-    ids = torch.arange(24, dtype=torch.int64).reshape(2, 3, 4)  # [world, n_q, k]
-    sc = torch.arange(24, dtype=torch.float32).reshape(2, 3, 4) * 0.5
-    bufs = torch.stack([pack_exchange(ids[w], sc[w]) for w in range(2)])
-    ci, cs = unpack_exchange(bufs.reshape(-1), 2, 3, 4)
+def test_plan_document_shards_weighted_by_rank_speed():
+    rows = [1024] * 1000
+    plan = plan_document_shards(rows, 4, weights=[1.0, 0.8, 1.0, 1.2])  # rank 1 scans 20 % slower, rank 3 20 % faster
+    sizes = [e - b for b, e in plan]
+    assert sum(sizes) == 1000 and sizes[1] < sizes[0] < sizes[3] and abs(sizes[1] - 200) <= 1 and abs(sizes[3] - 300) <= 1
+    with pytest.raises(ValueError):
+        plan_document_shards(rows, 4, weights=[1, 1, 0, 1])
+
+
+def test_exchange_layout_views_and_gather():
+    """The local top-k is written IN PLACE into [n_q*k int64 ids][n_q*k f32 scores]; the gathered buffer is world such blocks."""
+    n_q, k, world = 3, 4, 2
+    ids = torch.arange(24, dtype=torch.int64).reshape(world, n_q, k)
+    sc = torch.arange(24, dtype=torch.float32).reshape(world, n_q, k) * 0.5
+    bufs = []
+    for w in range(world):
+        b = torch.zeros(exchange_bytes(n_q, k), dtype=torch.uint8)
+        iv, sv = exchange_views(b, n_q, k)
+        iv.copy_(ids[w])
+        sv.copy_(sc[w])
+        assert b[: n_q * k * 8].view(torch.int64).tolist() == ids[w].reshape(-1).tolist()  # ids first, then scores
+        bufs.append(b)
+    ci, cs = gathered_candidates(torch.cat(bufs), world, n_q, k)
     assert ci.shape == (3, 8) and ci[1].tolist() == ids[0, 1].tolist() + ids[1, 1].tolist()
     assert cs[2].tolist() == sc[0, 2].tolist() + sc[1, 2].tolist()
 
@@ -44,8 +64,8 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _oracle_merge(cand_scores, cand_ids, k):
-    n_q = cand_scores.shape[0]
+def _oracle_merge(gathered, world, n_q, k):
+    cand_ids, cand_scores = gathered_candidates(gathered, world, n_q, k)
     ts = torch.full((n_q, k), float("-inf"))
     ti = torch.full((n_q, k), -1, dtype=torch.int64)
     tc = torch.zeros(n_q, dtype=torch.int32)
@@ -74,9 +94,9 @@ def _worker(rank, world, port, k, result_dir):
         p0, p1 = int(doc_first_page[plan[rank][0]]), int(doc_first_page[plan[rank][1]])
         my_pages, my_lens = pages[p0:p1], page_lens[p0:p1]
 
-        def local_search(q, q_lens, kk):  # oracle-backed stand-in for MaxSimIndex.search_device(id_base=p0)
-            ts = torch.full((len(q_lens), kk), float("-inf"))
-            ti = torch.full((len(q_lens), kk), -1, dtype=torch.int64)
+        def local_search(q, q_lens, kk, ti, ts):  # oracle-backed stand-in for the CUDA search writing the exchange views
+            ts.fill_(float("-inf"))
+            ti.fill_(-1)
             rows = np.concatenate(my_pages) if my_pages else np.zeros((0, 128), np.float32)
             off = orc.page_offsets(my_lens)
             qoff = np.concatenate([[0], np.cumsum(q_lens)])
@@ -85,7 +105,6 @@ def _worker(rank, world, port, k, result_dir):
                 a, b = orc.topk_np(s, kk)
                 ts[qi, :len(a)] = torch.from_numpy(a.astype(np.float32))
                 ti[qi, :len(b)] = torch.from_numpy(b + p0)
-            return ts, ti
 
         sharded = ShardedMaxSim(local_search, _oracle_merge)
         q = torch.from_numpy(np.concatenate(queries))
