@@ -72,18 +72,21 @@ def test_hamming_distance_batch_matches_reference_golden(golden_dir):
 
 
 # ------------------------------------------------------------------------------------------------ float MaxSim (a-7)
-@pytest.mark.parametrize("dtype,split4", [("bf16", 0), ("bf16", 2), ("int8", 0), ("int8", 2)])
-def test_single_group_forms_agree(dtype, split4):
-    """The replicated-query (split4) and the plain epilogue of maxsim_umma give bit-identical single-query scores."""
+@pytest.mark.parametrize("dtype", ["bf16", "int8", "fp8"])
+def test_host_transports_agree(dtype):
+    """b200ms_search_host moves small calls through mapped pinned memory (zero-copy) and batches through the copy engines:
+    same kernels, identical results; option zero_copy=0 forces the copy-engine transport."""
     rng = np.random.default_rng(77)
     lens = [1, 31, 32, 33, 0, 64, 127, 128, 129, 700, 1030, 2] + list(rng.integers(1, 400, size=40))
     pages = make_pages(rng, lens)
-    for t in (32, 5):
-        q = [unit_rows(rng, t)]
-        ref = MaxSimIndex(dtype=dtype); ref.set_option("split4", 1 if dtype == "int8" else 0); ref.set_option("unit_rows", 300)
-        alt = MaxSimIndex(dtype=dtype); alt.set_option("split4", split4); alt.set_option("unit_rows", 300)
-        ref.add_pages(pages); alt.add_pages(pages)
-        assert np.array_equal(ref.score_matrix(q), alt.score_matrix(q))
+    a = MaxSimIndex(dtype=dtype); a.add_pages(pages)
+    b = MaxSimIndex(dtype=dtype); b.set_option("zero_copy", 0); b.add_pages(pages)
+    allowed = rng.random(len(pages)) < 0.5
+    for qs in ([unit_rows(rng, 32)], [unit_rows(rng, 5)], [unit_rows(rng, t) for t in (32, 7, 40, 1)],
+               [unit_rows(rng, 32) for _ in range(12)]):  # 12 x 32 = 384 rows: above the zero-copy threshold on both
+        for mask in (None, a.mask_from_pages(allowed)):
+            ra, rb = a.search_host(qs, k=9, allow_mask=mask), b.search_host(qs, k=9, allow_mask=mask)
+            assert all(np.array_equal(x, y) for x, y in zip(ra, rb))
 
 
 def test_bf16_config0_shape_single_query():
@@ -137,20 +140,27 @@ def test_bf16_ragged_pages_empty_pages_unit_boundaries(unit_rows_):
 
 
 @pytest.mark.parametrize("dtype", ["bf16", "int8"])
-def test_w4_and_two_warpgroup_forms_agree(dtype):
-    """The four-epilogue-warpgroup kernel and the two-warpgroup kernel (the one-CTA forms, pair_cta = 0) are bit-identical."""
+def test_one_cta_forms_match_oracle(dtype):
+    """pair_cta = 0 (what a partition without whole TPCs falls back to): NM = 1 / 2 two-warpgroup kernel and the NM = 4 / 8
+    four-warpgroup kernel against the oracle -- bf16 within rounding, int8 bit-exact."""
     rng = np.random.default_rng(808)
     lens = [1, 33, 0, 64, 700, 1030, 2] + list(rng.integers(1, 300, size=50))
     pages = make_pages(rng, lens)
-    for n_q in (13, 32, 40):  # 4 tiles (bf16: NM=4; int8: NM=4), 8 tiles (int8: NM=8), 10 tiles (8 + phantom-padded 2)
+    rows = np.concatenate(pages)
+    off = orc.page_offsets(lens)
+    for n_q in (1, 5, 13, 32, 40):  # 1, 2, 4, 8 (int8: NM=8), 10 query tiles
         queries = [unit_rows(rng, 32 if i % 2 else 29) for i in range(n_q)]
-        a = MaxSimIndex(dtype=dtype); a.set_option("epi_w4", 1); b = MaxSimIndex(dtype=dtype); b.set_option("epi_w4", 0)
-        for i_ in (a, b):
-            i_.set_option("pair_cta", 0); i_.set_option("unit_rows", 400); i_.add_pages(pages)
-        assert np.array_equal(a.score_matrix(queries), b.score_matrix(queries)), (dtype, n_q)
+        a = MaxSimIndex(dtype=dtype); a.set_option("pair_cta", 0); a.set_option("unit_rows", 400); a.add_pages(pages)
+        got = a.score_matrix(queries)
+        if dtype == "bf16":
+            assert_close_rel(got, oracle_float(queries, pages), 3e-5)
+        else:
+            rq = orc.quantize_int8_np(rows, 127.0)
+            want = np.stack([orc.int8_maxsim_c(orc.quantize_int8_np(q, 127.0), rq, off) for q in queries])
+            assert np.array_equal(np.rint(got * 127.0 * 127.0).astype(np.int64), want), n_q
 
 
-@pytest.mark.parametrize("dtype", ["bf16", "int8"])
+@pytest.mark.parametrize("dtype", ["bf16", "int8", "fp8"])
 @pytest.mark.parametrize("unit_rows_,n_pages", [(400, 57), (64, 9), (4096, 3), (400, 1)])
 def test_cta_pair_form_agrees(dtype, unit_rows_, n_pages):
     """The CTA-pair kernel (tcgen05 cta_group::2, two unit streams per pair) is bit-identical to the one-CTA kernels:
@@ -207,6 +217,11 @@ def test_int8_bit_exact(n_q):
     lens = [1, 33, 0, 64, 200, 1024, 17, 96] + list(rng.integers(1, 260, size=30))
     pages = make_pages(rng, lens)
     queries = [unit_rows(rng, 32 if i % 3 else 19) for i in range(n_q)]
+    # every dot product of these tokens is negative (all-negative query x all-positive pages below): the per-chunk maximum
+    # is negative, which the epilogue's float-datapath max cannot order -> its exact integer fallback must kick in
+    queries[0] = -np.abs(queries[0])
+    for j in (3, 4, 9):
+        pages[j] = np.abs(pages[j])
     idx = MaxSimIndex(dtype="int8", i8_scale=127.0)
     idx.set_tuning(unit_rows=256)
     idx.add_pages(pages)
@@ -224,6 +239,8 @@ def test_int8_bit_exact(n_q):
         want = orc.int8_maxsim_c(orc.quantize_int8_np(q, 127.0), rows_q, off)
         got = raw[goff[qi]:goff[qi + 1]].sum(axis=0)
         assert np.array_equal(got, want), f"query {qi}"  # integer arithmetic: bit-exact
+        if qi == 0:
+            assert want[[3, 4, 9]].max() < 0  # the negative-maximum case really occurred
     ts, ti, tc = idx.search_host(queries, k=5)
     for qi, q in enumerate(queries):
         want = orc.int8_maxsim_c(orc.quantize_int8_np(q, 127.0), rows_q, off)
@@ -447,3 +464,165 @@ def test_properties_at_scale_int8_binary(dtype):
         _, oi = orc.topk_np(sb[qi], 10)
         assert ti[qi].tolist() == oi.tolist()
     assert ti[0][0] == 4242
+
+
+# ------------------------------------------------------------------------------------------------ fp8 e4m3 corpora (config-2 sweep point)
+def oracle_fp8(queries, pages, scale=64.0):
+    rows = np.concatenate(pages) if sum(len(p) for p in pages) else np.zeros((0, 128), np.float32)
+    off = orc.page_offsets([len(p) for p in pages])
+    rr = orc.dequantize_e4m3_np(orc.quantize_e4m3_np(rows, scale))
+    return np.stack([orc.float_maxsim_c(orc.dequantize_e4m3_np(orc.quantize_e4m3_np(q, scale)), rr, off) for q in queries]) / (scale * scale)
+
+
+@pytest.mark.parametrize("n_q", [1, 5, 13, 40])
+def test_fp8_matches_oracle(n_q):
+    """B200MS_F8: e4m3(x * 64) rows and queries, tcgen05 kind::f8f6f4 with fp32 accumulation.  The packed bytes equal the
+    oracle's round-to-nearest-even e4m3 codes; scores match the oracle's fp32 MaxSim of the dequantised values."""
+    rng = np.random.default_rng(300 + n_q)
+    lens = [1, 33, 0, 64, 200, 1024, 17, 96] + list(rng.integers(1, 260, size=30))
+    pages = make_pages(rng, lens)
+    pages[2 + 1][0, :4] = [7.5, -9.0, 1e-4, 0.0]  # saturation (7.5*64 > 448), subnormals, zero
+    queries = [unit_rows(rng, 32 if i % 3 else 19) for i in range(n_q)]
+    idx = MaxSimIndex(dtype="fp8")
+    assert idx.i8_scale == 64.0 and idx.row_bytes == 128
+    idx.set_tuning(unit_rows=256)
+    idx.add_pages(pages)
+    packed = idx.packed_rows().cpu().numpy()
+    codes = orc.quantize_e4m3_np(np.concatenate(pages), 64.0)
+    off_pad = np.concatenate([[0], np.cumsum([(n + 31) // 32 * 32 for n in lens])])
+    off = orc.page_offsets(lens)
+    for p in (0, 1, 3, 5, 7):
+        assert np.array_equal(packed[off_pad[p]:off_pad[p] + lens[p]], codes[off[p]:off[p + 1]])
+    got = idx.score_matrix(queries)
+    want = oracle_fp8(queries, pages)
+    assert_close_rel(got, want, 1e-4)  # products of e4m3 values are exact in fp32; only the summation order differs
+    ts, ti, tc = idx.search_host(queries, k=5)
+    for qi in range(n_q):
+        assert ti[qi].tolist() == orc.topk_np(got[qi].astype(np.float32), 5)[1].tolist()
+    # vs the unquantised fp32 MaxSim: the quantisation error of e4m3 (3 mantissa bits) stays within a few percent
+    full = oracle_float(queries, pages, bf16=False)
+    live = np.abs(full) > 0.5
+    assert (np.abs(got - full)[live] / np.abs(full)[live]).max() < 0.08
+
+
+# ------------------------------------------------------------------------------------------------ zero_pad_compat (SURVEY App. A.2)
+@pytest.mark.parametrize("case,batch", [("b", 128), ("c", 3)])
+def test_zero_pad_compat_matches_score_multi_vector_golden(golden_dir, case, batch):
+    """Product option zero_pad_compat=<batch size> reproduces colpali_engine score_multi_vector's padding quirk (a page
+    shorter than the longest of its batch scores max(true, 0) per token): golden cases B (one 128-batch) and C
+    (batch_size=3) were produced by the transformers port of score_multi_vector (tests/golden/make_golden.py)."""
+    fm = np.load(os.path.join(golden_dir, "float_maxsim.npz"))
+    lens = fm["b_lens"].tolist()
+    off = orc.page_offsets(lens)
+    pages = [fm["b_rows"][off[i]:off[i + 1]] for i in range(len(lens))]
+    queries = [fm["b_q0"], fm["b_q1"]]
+    want = fm[f"{case}_scores"]
+    idx = MaxSimIndex(dtype="bf16")
+    idx.set_option("zero_pad_compat", batch)
+    idx.add_pages(pages)
+    got = idx.score_matrix(queries)
+    assert_close_rel(got, want, BF16_RTOL)
+    # the quirk is visible: the all-negative query's clean MaxSim differs on the short pages
+    clean = MaxSimIndex(dtype="bf16"); clean.add_pages(pages)
+    assert np.abs(clean.score_matrix(queries)[0] - want[0]).max() > 0.1
+    # and against the oracle's own switch on bf16-rounded inputs (tight tolerance), batches of queries too (pair kernel)
+    many = queries + [unit_rows(np.random.default_rng(5), 32) * (-1 if i % 2 else 1) for i in range(11)]
+    rr = orc.bf16_round_np(fm["b_rows"])
+    want2 = np.stack([orc.float_maxsim_c(orc.bf16_round_np(q), rr, off, zero_pad_compat=True, batch=batch) for q in many])
+    assert_close_rel(idx.score_matrix(many), want2, 3e-5)
+    for pc in (0, 2):  # one-CTA and CTA-pair forms agree bit for bit
+        alt = MaxSimIndex(dtype="bf16"); alt.set_option("zero_pad_compat", batch); alt.set_option("pair_cta", pc); alt.add_pages(pages)
+        assert np.array_equal(alt.score_matrix(many), idx.score_matrix(many))
+
+
+def test_zero_pad_compat_rerank_batches_candidates_like_the_reference():
+    """In the two-stage path the reference scores ONE batch of <= 75 candidates in first-stage order
+    (fast_multivector_store.py:529,553-555): the clamp follows the candidate list, not the page ids."""
+    rng = np.random.default_rng(61)
+    lens = [int(x) for x in rng.integers(3, 90, size=40)]
+    pages = [np.abs(unit_rows(rng, n)) for n in lens]
+    q = -np.abs(unit_rows(rng, 20))  # every true maximum is negative: clamped pages score exactly 0
+    idx = MaxSimIndex(dtype="bf16")
+    idx.set_option("zero_pad_compat", 128)
+    idx.add_pages(pages)
+    cand = [17, 3, 29, 8, 11, 30, 2]
+    ci = torch.tensor([cand, cand[::-1]], dtype=torch.int64, device="cuda")
+    qd = torch.from_numpy(np.concatenate([q, q])).cuda()
+    ts, ti, tc = idx.rerank_batch(qd, [20, 20], ci, k=len(cand))
+    torch.cuda.synchronize()
+    sub = [pages[c] for c in cand]
+    want = orc.float_maxsim_c(orc.bf16_round_np(q), orc.bf16_round_np(np.concatenate(sub)),
+                              orc.page_offsets([len(p) for p in sub]), zero_pad_compat=True, batch=128)
+    longest = max(lens[c] for c in cand)
+    assert all((w == 0.0) == (lens[c] < longest) for w, c in zip(want, cand))
+    for row in range(2):
+        order = cand if row == 0 else cand[::-1]
+        w = {c: want[cand.index(c)] for c in cand}
+        exp = sorted(range(len(order)), key=lambda j: (-w[order[j]], j))
+        assert ti[row].cpu().tolist() == [order[j] for j in exp]
+        np.testing.assert_allclose(ts[row].cpu().numpy(), [w[order[j]] for j in exp], rtol=3e-5, atol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------------ batched rerank (per-query lists)
+@pytest.mark.parametrize("dtype", ["bf16", "int8", "binary"])
+def test_rerank_batch_per_query_candidate_lists(dtype):
+    rng = np.random.default_rng(71)
+    lens = [int(x) for x in rng.integers(1, 200, size=120)] + [0, 1024]
+    pages = make_pages(rng, lens)
+    t_list = [32, 7, 40, 32, 1, 33, 64, 20, 32]  # queries of 1-2 groups: tiles shared by several queries and straddled
+    queries = [unit_rows(rng, t) for t in t_list]
+    idx = MaxSimIndex(dtype=dtype)
+    idx.add_pages(pages)
+    full = idx.score_matrix(queries)
+    n_cand, k = 37, 10
+    cand = np.stack([rng.permutation(len(pages))[:n_cand] for _ in queries]).astype(np.int64)
+    cand[1, 5] = cand[4, 0] = cand[4, 36] = -1  # unused slots
+    qd = torch.from_numpy(np.concatenate(queries)).cuda()
+    ts, ti, tc = idx.rerank_batch(qd, t_list, torch.from_numpy(cand).cuda(), k)
+    torch.cuda.synchronize()
+    ts, ti, tc = ts.cpu().numpy(), ti.cpu().numpy(), tc.cpu().numpy()
+    for qi in range(len(queries)):
+        valid = [j for j in range(n_cand) if cand[qi, j] >= 0]
+        order = sorted(valid, key=lambda j: (-full[qi, cand[qi, j]], j))[:k]
+        assert tc[qi] == len(order) and ti[qi][:len(order)].tolist() == [int(cand[qi, j]) for j in order], (dtype, qi)
+        np.testing.assert_allclose(ts[qi][:len(order)], [full[qi, cand[qi, j]] for j in order], rtol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------------ pipelined sharded search, world = 1
+def test_sharded_search_pipeline_world1_matches_search():
+    """b200ms_sharded_search_begin/_end and the *_host_* forms with a one-rank communicator: same answer as
+    b200ms_search_device, two tickets in flight, results one step late."""
+    rng = np.random.default_rng(81)
+    pages = make_pages(rng, list(rng.integers(1, 200, size=300)))
+    idx = MaxSimIndex(dtype="bf16")
+    idx.add_pages(pages)
+    idx.comm_init(b"\0" * 128, 0, 1)
+    batches = [[unit_rows(rng, 32) for _ in range(nq)] for nq in (3, 12, 1, 5)]
+    base = 7 << 40
+    want = [idx.search_host(b, k=8, id_base=base) for b in batches]
+    outs, tickets = [], []
+    for b in batches:  # at most two in flight: end(i-1) right after begin(i)
+        qd = torch.from_numpy(np.concatenate(b)).cuda()
+        out = (torch.empty((len(b), 8), device="cuda"), torch.empty((len(b), 8), dtype=torch.int64, device="cuda"),
+               torch.empty((len(b),), dtype=torch.int32, device="cuda"))
+        tickets.append(idx.sharded_search_begin(qd, [len(x) for x in b], 8, base, out))
+        outs.append(out)
+        if len(tickets) >= 2:
+            idx.sharded_search_end(tickets[-2])
+    idx.sharded_search_end(tickets[-1])
+    torch.cuda.synchronize()
+    for (ws, wi, wc), (ts, ti, tc) in zip(want, outs):
+        assert np.array_equal(ti.cpu().numpy(), wi) and np.array_equal(ts.cpu().numpy(), ws) and np.array_equal(tc.cpu().numpy(), wc)
+    # host pipeline
+    t_prev, prev = None, None
+    for b, (ws, wi, wc) in zip(batches, want):
+        qh = torch.from_numpy(np.concatenate(b)).pin_memory()
+        t = idx.sharded_search_host_begin(qh, [len(x) for x in b], 8, base)
+        if t_prev is not None:
+            o = (torch.empty((len(prev[0]), 8)), torch.empty((len(prev[0]), 8), dtype=torch.int64), torch.empty((len(prev[0]),), dtype=torch.int32))
+            idx.sharded_search_host_end(t_prev, *o)
+            assert np.array_equal(o[1].numpy(), prev[1][1]) and np.array_equal(o[0].numpy(), prev[1][0])
+        t_prev, prev = t, (b, (ws, wi, wc))
+    o = (torch.empty((len(prev[0]), 8)), torch.empty((len(prev[0]), 8), dtype=torch.int64), torch.empty((len(prev[0]),), dtype=torch.int32))
+    idx.sharded_search_host_end(t_prev, *o)
+    assert np.array_equal(o[1].numpy(), prev[1][1]) and np.array_equal(o[2].numpy(), prev[1][2])

@@ -69,6 +69,23 @@ def _worker(rank, world, port, mode, result_dir):
             ws, wi = orc.topk_np(want, k)
             assert ti[qi].tolist() == wi.tolist(), (rank, qi, ti[qi].tolist(), wi.tolist())
             np.testing.assert_allclose(ts[qi], ws, rtol=3e-5)
+        # pipelined form: three steps, two tickets in flight, each step's result picked up one step later
+        outs, tickets = [], []
+        for step in range(3):
+            t, out = sharded.begin(q, [len(x) for x in queries], k)
+            tickets.append(t)
+            outs.append(out)
+            if step:
+                sharded.end(tickets[step - 1])
+        sharded.end(tickets[-1])
+        torch.cuda.synchronize()
+        for o in outs:
+            assert np.array_equal(o[1].cpu().numpy(), ti) and np.array_equal(o[0].cpu().numpy(), ts)
+        # every rank holds the identical merged list (all-reduce of a checksum)
+        chk = torch.stack([outs[-1][1].sum(), outs[-1][1].sum()]).double()
+        lo, hi = chk.clone(), chk.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        assert torch.equal(lo, hi)
         open(os.path.join(result_dir, f"ok{rank}"), "w").write("ok")
     finally:
         dist.destroy_process_group()
@@ -149,6 +166,61 @@ def _store_worker(rank, world, port, result_dir):
         open(os.path.join(result_dir, "ok0"), "w").write("ok")
     finally:
         dist.destroy_process_group()
+
+
+def _two_stage_store_worker(rank, world, port, result_dir):
+    import asyncio
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from morphik_core_b200.models import DocumentChunk
+        from morphik_core_b200.sharded_store import ShardedB200MultiVectorStore
+        from oracle import maxsim_oracle as orc
+
+        # fde_candidates larger than any shard: the two-stage path degenerates to the exhaustive answer (checkable)
+        store = ShardedB200MultiVectorStore(mode="bf16", fde_candidates=500)
+        if rank != 0:
+            store.worker_loop()
+            open(os.path.join(result_dir, f"ok{rank}"), "w").write("ok")
+            return
+        run = asyncio.run
+        rng = np.random.default_rng(37)
+        docs = {}
+        for d in range(40):
+            pages = []
+            for _ in range(int(rng.integers(2, 6))):
+                x = rng.standard_normal((int(rng.integers(32, 200)), 128)).astype(np.float32)
+                pages.append(x / np.linalg.norm(x, axis=1, keepdims=True))
+            docs[f"doc{d}"] = pages
+            run(store.store_embeddings([DocumentChunk(document_id=f"doc{d}", content=f"{d}/{j}", embedding=p, chunk_number=j)
+                                        for j, p in enumerate(pages)]))
+        flat = [(d, j, p) for d, ps in docs.items() for j, p in enumerate(ps)]
+        rows = orc.bf16_round_np(np.concatenate([p for _, _, p in flat]))
+        off = orc.page_offsets([len(p) for _, _, p in flat])
+        for t in (32, 20):
+            q = rng.standard_normal((t, 128)).astype(np.float32)
+            s = orc.float_maxsim_c(orc.bf16_round_np(q), rows, off)
+            order = np.argsort(-s.astype(np.float64), kind="stable")[:7]
+            res = run(store.query_similar(q, k=7))
+            assert [(r.document_id, r.chunk_number) for r in res] == [(flat[i][0], flat[i][1]) for i in order]
+            np.testing.assert_allclose([r.score for r in res], s[order], rtol=3e-5)
+        assert {"encode_query_ms", "ns_query_ms", "rerank_scoring_ms", "total_ms"} <= set(store.last_query_timing)
+        on1 = [d for d, r in store.doc_rank.items() if r == 1][:5]
+        res = run(store.query_similar(q, k=30, doc_ids=on1))
+        assert {r.document_id for r in res} <= set(on1) and len(res) == min(30, sum(len(docs[d]) for d in on1))
+        store.close()
+        open(os.path.join(result_dir, "ok0"), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_two_stage_store_world2_nccl(tmp_path):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    mp.spawn(_two_stage_store_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    assert sorted(os.listdir(tmp_path)) == ["ok0", "ok1"]
 
 
 def test_sharded_store_world2_nccl(tmp_path):

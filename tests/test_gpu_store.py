@@ -26,7 +26,7 @@ def get_sample_embeddings(num_vectors=3, dim=128, seed=0):  # test_multivector.p
     return torch.rand((num_vectors, dim), generator=g) * 2 - 1
 
 
-@pytest.fixture(params=["binary", "bf16", "int8"])
+@pytest.fixture(params=["binary", "bf16", "int8", "fp8"])
 def vector_store(request):
     store = B200MultiVectorStore(mode=request.param)
     yield store
@@ -256,3 +256,91 @@ def test_concurrent_queries_are_serialised_and_consistent():
     sequential = [run(store.query_similar(q, k=3)) for q in queries]
     assert [[(c.document_id, c.score) for c in r] for r in results] == [[(c.document_id, c.score) for c in r] for r in sequential]
     store.close()
+
+
+def _page_chunks(rng, doc, n_pages, lo=3, hi=90):
+    out = []
+    for j in range(n_pages):
+        x = rng.standard_normal((int(rng.integers(lo, hi)), 128)).astype(np.float32)
+        x = torch.from_numpy(x / np.linalg.norm(x, axis=1, keepdims=True)).bfloat16().float().numpy()  # bf16-valued like ColPali output
+        out.append(DocumentChunk(document_id=doc, content=f"{doc}/{j}", embedding=x, chunk_number=j, metadata={"j": j}))
+    return out
+
+
+@pytest.mark.parametrize("mode,fde_candidates", [("bf16", None), ("binary", None), ("bf16", 64), ("int8", 64)])
+def test_journaled_store_appends_and_replays(tmp_path, mode, fde_candidates):
+    """every store_embeddings call becomes an append-only segment, every delete a tombstone line; reopening the
+    directory replays them in order (incl. delete-then-reinsert of the same document) without rewriting anything."""
+    import os
+
+    rng = np.random.default_rng(17)
+    d = str(tmp_path / "store")
+    kw = dict(mode=mode, fde_candidates=fde_candidates, compact_dead_fraction=0.9)
+    s = B200MultiVectorStore.open(d, **kw)
+    docs = {f"doc{i}": _page_chunks(rng, f"doc{i}", int(rng.integers(1, 5))) for i in range(10)}
+    for name, chunks in docs.items():
+        run(s.store_embeddings(chunks, app_id="app"))
+    sizes = {f: os.path.getsize(os.path.join(d, f)) for f in os.listdir(d) if f.endswith(".b2ms")}
+    assert len(sizes) == 10
+    assert run(s.delete_chunks_by_document_id("doc3")) and run(s.delete_chunks_by_document_id("doc7"))
+    docs["doc3"] = _page_chunks(rng, "doc3", 2)  # re-insert after the tombstone: must survive the replay
+    run(s.store_embeddings(docs["doc3"], app_id="app"))
+    docs.pop("doc7")
+    assert {f: os.path.getsize(os.path.join(d, f)) for f in sizes} == sizes  # nothing was rewritten
+    q = docs["doc5"][0].embedding
+    want = [(r.document_id, r.chunk_number, r.score) for r in run(s.query_similar(q, k=8, app_id="app"))]
+    assert want[0][:2] == ("doc5", 0) and all(x[0] != "doc7" for x in want)
+    s.close()
+    s2 = B200MultiVectorStore.open(d, **kw)
+    got = [(r.document_id, r.chunk_number, r.score) for r in run(s2.query_similar(q, k=8, app_id="app"))]
+    assert got == want
+    assert run(s2.get_chunks_by_id([("doc3", 1), ("doc7", 0)]))[0].content == "doc3/1"
+    assert len(run(s2.get_chunks_by_id([("doc7", 0)]))) == 0
+    # checkpoint: one base segment, empty tombstone log, same answers
+    s2.save(d)
+    assert sorted(f for f in os.listdir(d) if f.endswith(".b2ms")) == ["corpus.b2ms", "seg-000001.b2ms"]
+    run(s2.store_embeddings(_page_chunks(rng, "late", 1), app_id="app"))
+    s2.close()
+    s3 = B200MultiVectorStore.open(d, **kw)
+    assert [(r.document_id, r.chunk_number, r.score) for r in run(s3.query_similar(q, k=8, app_id="app", doc_ids=list(docs)))] == want
+    assert run(s3.get_chunks_by_id([("late", 0)]))[0].content == "late/0"
+    s3.close()
+
+
+def test_load_with_fde_candidates_rebuilds_two_stage(tmp_path):
+    rng = np.random.default_rng(23)
+    s = B200MultiVectorStore(mode="bf16")
+    for i in range(30):
+        run(s.store_embeddings(_page_chunks(rng, f"d{i}", 3, lo=32, hi=120)))
+    q = s.catalog.records[40]
+    qe = _page_chunks(np.random.default_rng(1), "q", 1)[0].embedding[:20]
+    want = [(r.document_id, r.chunk_number) for r in run(s.query_similar(qe, k=5))]
+    s.save(str(tmp_path))
+    two = B200MultiVectorStore.load(str(tmp_path), fde_candidates=90)  # 90 candidates = the whole corpus: exhaustive answer
+    assert two._two_stage is not None and two._two_stage.n_pages == 90
+    assert [(r.document_id, r.chunk_number) for r in run(two.query_similar(qe, k=5))] == want
+    assert {"encode_query_ms", "ns_query_ms", "load_multivectors_ms", "rerank_scoring_ms", "build_chunks_ms", "total_ms"} <= set(
+        two.last_query_timing) or two.coalesce_queries
+    res = run(two.query_similar_batch([qe], k=5))
+    assert {"encode_query_ms", "ns_query_ms", "rerank_scoring_ms", "build_chunks_ms", "total_ms"} <= set(two.last_query_timing)
+    assert [(r.document_id, r.chunk_number) for r in res[0]] == want
+    s.close(); two.close()
+
+
+def test_store_zero_pad_compat_option():
+    """B200MultiVectorStore(zero_pad_compat=128) scores like the reference's padded batches."""
+    rng = np.random.default_rng(29)
+    lens = [5, 64, 1, 33, 64, 17, 40, 2]
+    pages = [np.abs(rng.standard_normal((n, 128))).astype(np.float32) for n in lens]
+    pages = [p / np.linalg.norm(p, axis=1, keepdims=True) for p in pages]
+    q = -np.abs(rng.standard_normal((8, 128))).astype(np.float32)
+    s = B200MultiVectorStore(mode="bf16", zero_pad_compat=128)
+    run(s.store_embeddings([DocumentChunk(document_id=f"d{i}", content="", embedding=p, chunk_number=0) for i, p in enumerate(pages)]))
+    res = run(s.query_similar(q, k=8))
+    want = orc.float_maxsim_c(orc.bf16_round_np(q), orc.bf16_round_np(np.concatenate(pages)), orc.page_offsets(lens),
+                              zero_pad_compat=True, batch=128)
+    got = {r.document_id: r.score for r in res}
+    for i in range(8):
+        assert abs(got[f"d{i}"] - want[i]) <= 3e-5 * max(1.0, abs(want[i]))
+    assert all(got[f"d{i}"] == 0.0 for i in range(8) if lens[i] < 64) and all(got[f"d{i}"] < 0 for i in (1, 4))
+    s.close()
