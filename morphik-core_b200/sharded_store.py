@@ -233,21 +233,22 @@ class ShardedB200MultiVectorStore(QueryCoalescer, BaseVectorStore):
             recs, lens = payload["recs"], payload["lens"]
             mine = self._rows_to_owner(rows, n_rows, owner)
             err = None
-            try:
+            try:  # phase 1: the only step that can fail -- the owner packs the pages into its shard
                 if owner == self.rank:
                     off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
                     (self._two_stage or self.index).add_pages([mine[off[i]:off[i + 1]] for i in range(n_items)])
-                for (doc, _num, _app) in recs:
-                    self.doc_rank[doc] = owner
-                self.rank_rows[owner] += int(sum(lens))
-                if owner in self.catalogs:  # the owner's own catalogue and rank 0's mirror, in command-stream order
-                    extra = self._pending_payloads if self.rank == 0 else None
-                    for i, ((doc, num, app), n) in enumerate(zip(recs, lens)):
-                        content, meta = extra[i] if extra is not None else ("", {})
-                        self.catalogs[owner].add(PageRecord(doc, int(num), content, meta, app, int(n)))
             except Exception as e:  # noqa: BLE001  (reported through _agree; the collective stream stays in step)
                 err = e
-            self._agree(err)
+            self._agree(err)  # raises on every rank if the owner failed: nobody has touched its bookkeeping yet
+            # phase 2: bookkeeping, identical on every rank and in command-stream order (rank 0's mirror included)
+            for (doc, _num, _app) in recs:
+                self.doc_rank[doc] = owner
+            self.rank_rows[owner] += int(sum(lens))
+            if owner in self.catalogs:
+                extra = self._pending_payloads if self.rank == 0 else None
+                for i, ((doc, num, app), n) in enumerate(zip(recs, lens)):
+                    content, meta = extra[i] if extra is not None else ("", {})
+                    self.catalogs[owner].add(PageRecord(doc, int(num), content, meta, app, int(n)))
             return None
         if op == OP_QUERY:
             k, n_q, n_rows = hdr[5], hdr[6], hdr[3]

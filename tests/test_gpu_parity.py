@@ -502,6 +502,7 @@ def test_fp8_matches_oracle(n_q):
     # vs the unquantised fp32 MaxSim: the quantisation error of e4m3 (3 mantissa bits) stays within a few percent
     full = oracle_float(queries, pages, bf16=False)
     live = np.abs(full) > 0.5
+    live[:, 3] = False  # page 3 carries the deliberately saturated / subnormal row
     assert (np.abs(got - full)[live] / np.abs(full)[live]).max() < 0.08
 
 

@@ -25,7 +25,10 @@ class OracleShardIndex:
 
     def add_pages(self, pages):
         first = len(self.pages)
-        self.pages.extend(np.asarray(p, dtype=np.float32) for p in pages)
+        new = [np.asarray(p, dtype=np.float32) for p in pages]
+        if any(len(p) and float(p[0, 0]) == 12345.0 for p in new):  # test hook: "this rank cannot take these pages"
+            raise MemoryError("simulated allocation failure")
+        self.pages.extend(new)
         return first, len(pages)
 
     def compact(self, keep):
@@ -146,6 +149,40 @@ def _worker(rank, world, port, out_dir):
         assert [(r.document_id, r.chunk_number) for r in res] == oracle(q, 8)[0]
         assert run(store.get_chunks_by_id([("doc7", 0)])) == [] and len(run(store.get_chunks_by_id([("doc1", 0), ("doc1", 0)]))) == 1
         assert split_global_id((1 << 40) | 17) == (1, 17)
+        # a k beyond the merge capacity (world * k <= 8192) is truncated, not fatal (ADVICE: large-k query killed the store)
+        res = run(store.query_similar(q, k=5000))
+        assert len(res) == sum(len(p) for p in docs.values())
+        # a failure on ONE rank (here: the owner's add_pages) surfaces on rank 0 and the command stream stays in step
+        from morphik_core_b200.sharded_store import ShardedStoreError
+
+        bad = np.full((4, 128), 12345.0, dtype=np.float32)
+        for attempt in range(2):  # whichever rank is least loaded owns it: both ranks' failures must be survivable
+            with pytest.raises(ShardedStoreError):
+                run(store.store_embeddings([DocumentChunk(document_id=f"bad{attempt}", content="x", embedding=bad, chunk_number=0)]))
+        res = run(store.query_similar(q, k=8))
+        assert [(r.document_id, r.chunk_number) for r in res] == oracle(q, 8)[0]
+        assert "bad0" not in store.doc_rank and all(c.lookup("bad0", 0) is None for c in store.catalogs.values())
+        # concurrent writers and readers (ADVICE high: mirror vs index order): catalogue order == index order afterwards
+        new_docs = {f"new{d}": [rng.standard_normal((int(rng.integers(3, 30)), 128)).astype(np.float32) for _ in range(2)] for d in range(8)}
+
+        async def storm():
+            writes = [store.store_embeddings([DocumentChunk(document_id=d, content=f"{d}/{j}", embedding=p, chunk_number=j, metadata={"j": j})
+                                              for j, p in enumerate(ps)], app_id="app") for d, ps in new_docs.items()]
+            reads = [store.query_similar(q, k=5) for _ in range(6)]
+            return await asyncio.gather(*writes, *reads)
+
+        run(storm())
+        docs.update(new_docs)
+        for d, ps in new_docs.items():
+            r = store.doc_rank[d]
+            for j, p in enumerate(ps):
+                pid = store.catalogs[r].lookup(d, j)
+                assert pid is not None and store.catalogs[r].records[pid].n_rows == len(p)
+        for name in ("new3", "new6"):  # documents that landed on either rank resolve to their own payloads
+            q2 = new_docs[name][1]
+            res = run(store.query_similar(q2, k=9))
+            assert [(r.document_id, r.chunk_number) for r in res] == oracle(q2, 9)[0] and res[0].content == f"{name}/1"
+        assert {store.doc_rank[d] for d in new_docs} == {0, 1}
         store.close()
         open(os.path.join(out_dir, "ok0"), "w").write("ok")
     finally:

@@ -2,9 +2,11 @@
 
 Builds a synthetic shard (default 32768 pages x 1024 x 128, 8.6 GB bf16) and launches each scoring kernel a few times
 in a fixed order so that `ncu -k regex:<name> -s <skip> -c <count>` picks a warm launch:
-  bf16:   4x bq=32 (2 launches of maxsim_umma<0,4> each), then 4x bq=1 (maxsim_umma<0,1>)
-  int8:   4x bq=32 (maxsim_umma<1,8>), 4x bq=1 (maxsim_umma<1,1>)          [--int8]
-  binary: 4x bq=8 (maxsim_b1<8>), 4x bq=1 (maxsim_b1<1>)                   [--binary]
+  (default)     bf16: 4x bq=32 (maxsim_umma_pair<0,4>), then 4x bq=1 (maxsim_umma<0,1>)
+  --only int8   int8 sub-shard: 4x bq=32 (maxsim_umma_pair<1,4>), 4x bq=1
+  --only fp8    fp8 sub-shard, same
+  --only binary 1-bit sub-shard: 4x bq=8 (tcgen05 path), 4x bq=1 (POPC path)
+  --only fde    FDE matrix of the shard: 4x scan with 1 query, 4x with 32 queries (fde_scan_umma_kernel)
 """
 import argparse
 import os
@@ -19,10 +21,9 @@ from morphik_core_b200.index import MaxSimIndex  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--pages", type=int, default=32768)
-ap.add_argument("--int8", action="store_true")
-ap.add_argument("--binary", action="store_true")
+ap.add_argument("--only", choices=["bf16", "int8", "fp8", "binary", "fde"], default="bf16")
 ap.add_argument("--reps", type=int, default=4)
-ap.add_argument("--bqs", type=str, default="32,1", help="query batch sizes to drive (bf16 / int8)")
+ap.add_argument("--bqs", type=str, default="32,1", help="query batch sizes to drive")
 args = ap.parse_args()
 
 dev = torch.device("cuda", 0)
@@ -42,29 +43,24 @@ def drive(idx, bqs):
         print(f"{idx.dtype_name} bq={bq}: score ms {['%.3f' % m for m in ms]}", flush=True)
 
 
-idx = MaxSimIndex(dtype="bf16")
-idx.adopt_packed(packed, lens)
-drive(idx, [int(b) for b in args.bqs.split(",")])
-rows = packed.view(torch.bfloat16).view(-1, 128)
-if args.int8:
-    i8 = MaxSimIndex(dtype="int8")
-    buf = torch.empty(rows.shape[0] * 128 + 1024, dtype=torch.uint8, device=dev)
-    off = (-buf.data_ptr()) % 1024
-    p8 = buf[off:off + rows.shape[0] * 128]
-    step = 1 << 22
-    for r0 in range(0, rows.shape[0], step):
-        p8.view(torch.int8).view(-1, 128)[r0:r0 + step] = torch.clamp(torch.round(rows[r0:r0 + step].float() * 127.0), -127, 127).to(torch.int8)
-    i8.adopt_packed(p8, lens)
-    drive(i8, [int(b) for b in args.bqs.split(",")])
-if args.binary:
-    b1 = MaxSimIndex(dtype="binary")
-    bits = torch.empty((rows.shape[0], 16), dtype=torch.uint8, device=dev)
-    step = 1 << 22
-    for r0 in range(0, rows.shape[0], step):
-        bits[r0:r0 + step] = b1.sign_pack(rows[r0:r0 + step])
-    braw = torch.empty(bits.numel() + 1024, dtype=torch.uint8, device=dev)
-    off = (-braw.data_ptr()) % 1024
-    pb = braw[off:off + bits.numel()]
-    pb.copy_(bits.reshape(-1))
-    b1.adopt_packed(pb, lens)
-    drive(b1, [8, 1])
+if args.only == "bf16":
+    idx = MaxSimIndex(dtype="bf16")
+    idx.adopt_packed(packed, lens)
+    drive(idx, [int(b) for b in args.bqs.split(",")])
+elif args.only in ("int8", "fp8"):
+    drive(bench.quantised_subshard(packed, args.pages, args.only, 0), [int(b) for b in args.bqs.split(",")])
+elif args.only == "binary":
+    drive(bench.quantised_subshard(packed, args.pages, "binary", 0), [8, 1])
+else:
+    from morphik_core_b200.fde import TwoStageIndex
+
+    sub = MaxSimIndex(dtype="bf16")
+    sub.adopt_packed(packed, lens)
+    two = TwoStageIndex(index=sub)
+    two.rebuild_from_index()
+    for nq in (1, 32):
+        qf = torch.randn((nq, two.fde_dim), device=dev)
+        for _ in range(args.reps):
+            two.fde_scores(qf)
+        torch.cuda.synchronize()
+        print(f"fde scan n_q={nq} done", flush=True)
