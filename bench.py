@@ -258,8 +258,9 @@ def config0_latency(packed, q_pin, out_pin, k, skip_cpu, n_pages=100, iters=300)
     o = (out_pin[0][:1], out_pin[1][:1], out_pin[2][:1])
     out = {"workload": f"configs[0]: {n_pages} pages x {P_PATCH} patches x {DIM}-d bf16, 1 query x {T_TOK} tokens, top-{k}",
            "api": "b200ms_search_host (host query in, host top-k out)", "calls": iters}
-    for label, zc in (("", 1), ("copy_engine_", 0)):
+    for label, zc, gr in (("", 1, 1), ("no_graph_", 1, 0), ("copy_engine_", 0, 0)):
         idx0.set_option("zero_copy", zc)
+        idx0.set_option("host_graph", gr)
         for _ in range(20):
             idx0.search_host_flat(q1, [T_TOK], k, *o)
         lat = []
@@ -272,7 +273,9 @@ def config0_latency(packed, q_pin, out_pin, k, skip_cpu, n_pages=100, iters=300)
         out[label + "e2e_p95_us"] = float(lat[int(len(lat) * 0.95)])
     kern = idx0.score_times_ms(64)
     out["scoring_kernel_us"] = 1e3 * sum(kern) / len(kern)
-    out["transport"] = "zero-copy through mapped pinned memory (default for <= 256 query rows); copy_engine_* = cudaMemcpyAsync path"
+    out["transport"] = ("default: query + metadata written to a mapped pinned block the kernels read in place, results written back the same way, "
+                        "pack -> score -> top-k replayed as ONE CUDA graph; no_graph_* = the same with three plain launches; "
+                        "copy_engine_* = cudaMemcpyAsync H2D / D2H")
     if not skip_cpu:
         from oracle import maxsim_oracle as orc
 

@@ -28,6 +28,10 @@ int check_cuda(b200ms_t* h, cudaError_t e, const char* what) {
 
 int reserve(b200ms_t* h, DeviceBuf& b, size_t bytes) {
   if (bytes <= b.cap) return B200MS_OK;
+  if (h) {
+    if (h->capturing) return set_error(h, B200MS_ESTATE, "scratch buffer would grow inside a graph capture");
+    h->generation++;  // captured graphs hold the old address
+  }
   if (b.p) cudaFree(b.p);
   b.p = nullptr;
   b.cap = 0;
@@ -48,6 +52,7 @@ int reserve(b200ms_t* h, DeviceBuf& b, size_t bytes) {
 
 int reserve_pinned(b200ms_t* h, PinnedBuf& b, size_t bytes) {
   if (bytes <= b.cap) return B200MS_OK;
+  if (h) h->generation++;
   if (b.p) cudaFreeHost(b.p);
   b.p = nullptr;
   b.cap = 0;
@@ -59,6 +64,14 @@ int reserve_pinned(b200ms_t* h, PinnedBuf& b, size_t bytes) {
     return set_error(h, B200MS_ENOMEM, "cudaHostAlloc of " + std::to_string(want) + " pinned bytes failed");
   }
   b.cap = want;
+  return B200MS_OK;
+}
+
+int ensure_smem(b200ms_t* h, const void* kernel, int smem, const char* what) {
+  auto it = h->smem_attr.find(kernel);
+  if (it != h->smem_attr.end() && it->second >= smem) return B200MS_OK;
+  if (int e = check_cuda(h, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), what)) return e;
+  h->smem_attr[kernel] = smem;
   return B200MS_OK;
 }
 
@@ -228,6 +241,8 @@ B200MS_API int b200ms_destroy(b200ms_t* h) {
   DeviceGuard g(h->device);
   cudaDeviceSynchronize();
   comm_teardown(h);
+  for (auto& g2 : h->host_graphs)
+    if (g2.exec) cudaGraphExecDestroy(g2.exec);
   DeviceBuf* bufs[] = {&h->chunk_page, &h->unit_start, &h->page_start, &h->page_len, &h->clamp_pages, &h->clamp_slots,
                        &h->meta, &h->meta_b, &h->q_raw, &h->q_packed, &h->scores, &h->mask, &h->mask_index, &h->out_all,
                        &h->cand_pad, &h->cand_start, &h->cand_end, &h->cand_mask, &h->topk_keys, &h->topk_ids, &h->b1_q_i8, &h->b1_tok_const,
@@ -292,6 +307,8 @@ B200MS_API int b200ms_set_option(b200ms_t* h, const char* name, int64_t value) {
     h->zero_copy = int(value);
   } else if (n == "fde_gemm" && value >= 0 && value <= 1) {
     h->fde_gemm = int(value);
+  } else if (n == "host_graph" && value >= 0 && value <= 1) {
+    h->host_graph = int(value);
   } else if (n == "unit_rows" && value > 0) {
     h->unit_rows = value;
   } else if (n == "max_ctas" && value >= 0) {
@@ -299,6 +316,7 @@ B200MS_API int b200ms_set_option(b200ms_t* h, const char* name, int64_t value) {
   } else {
     return set_error(h, B200MS_EINVAL, "set_option: unknown option or bad value: " + n);
   }
+  h->generation++;
   return B200MS_OK;
 }
 
@@ -440,6 +458,7 @@ B200MS_API int b200ms_set_corpus(b200ms_t* h, const void* rows, int dtype, const
   }
   if (int e = check_cuda(h, cudaStreamSynchronize(s), "set_corpus: stream sync")) return e;
   h->corpus = c;
+  h->generation++;
   return B200MS_OK;
 }
 
@@ -500,7 +519,8 @@ static int score_impl(b200ms_t* h, const void* q_packed, int n_groups, const int
     const bool tensor_path = !cs.ids && (h->b1_tensor == 1 || (h->b1_tensor == 2 && n_groups >= 2));
     if ((tensor_path && c.has_empty) || cs.per_query)
       if (int e = check_cuda(h, cudaMemsetAsync(group_scores, 0, size_t(n_groups_padded) * size_t(ld) * 4, s), "score: memset")) return e;
-    if (int e = check_cuda(h, cudaEventRecord(h->ev0[slot], s), "score: event record")) return e;
+    if (!h->capturing)
+      if (int e = check_cuda(h, cudaEventRecord(h->ev0[slot], s), "score: event record")) return e;
     if (tensor_path) {
       if (int e = launch_score_b1_umma(h, q_packed, ntok_dev, n_groups, group_scores, ld, s)) return e;
     } else if (cs.per_query) {
@@ -513,8 +533,10 @@ static int score_impl(b200ms_t* h, const void* q_packed, int n_groups, const int
     } else {
       if (int e = launch_score_b1(h, cs.ids, cs.n_cand, q_packed, n_groups, ntok_dev, group_scores, ld, s, 0, n_groups)) return e;
     }
-    if (int e = check_cuda(h, cudaEventRecord(h->ev1[slot], s), "score: event record")) return e;
-    h->ev_count++;
+    if (!h->capturing) {
+      if (int e = check_cuda(h, cudaEventRecord(h->ev1[slot], s), "score: event record")) return e;
+      h->ev_count++;
+    }
     return B200MS_OK;
   }
   // pages with zero rows (and unused candidate slots) are never touched by the tile kernel: they score 0
@@ -549,7 +571,8 @@ static int score_impl(b200ms_t* h, const void* q_packed, int n_groups, const int
     plan.slot_mode = 0;
     if (int e = ensure_clamp_pages(h, s, &plan.clamp_bits)) return e;
   }
-  if (int e = check_cuda(h, cudaEventRecord(h->ev0[slot], s), "score: event record")) return e;
+  if (!h->capturing)
+    if (int e = check_cuda(h, cudaEventRecord(h->ev0[slot], s), "score: event record")) return e;
   if (cs.ids && cs.per_query) {
     // one launch per 128-token query tile: the tile's queries against THEIR candidate lists only (a contiguous slot range)
     const int n_mtiles = n_groups_padded / 4;
@@ -572,8 +595,10 @@ static int score_impl(b200ms_t* h, const void* q_packed, int n_groups, const int
   } else {
     if (int e = launch_score_umma(h, &plan, q_packed, n_groups, group_scores, ld, s)) return e;
   }
-  if (int e = check_cuda(h, cudaEventRecord(h->ev1[slot], s), "score: event record")) return e;
-  h->ev_count++;
+  if (!h->capturing) {
+    if (int e = check_cuda(h, cudaEventRecord(h->ev1[slot], s), "score: event record")) return e;
+    h->ev_count++;
+  }
   return B200MS_OK;
 }
 
@@ -826,10 +851,88 @@ static int search_host_impl(b200ms_t* h, const float* q_host, const int32_t* q_l
   if (zc) {
     memcpy(st + meta_off, m.host.data(), m.host.size());
     if (q_bytes) memcpy(st + q_off, q_host, q_bytes);
-    e = search_core(h, st + q_off, B200MS_F32, q_lens, n_q, k, allow_dev, i8_q_scale, score_scale, id_base,
-                    reinterpret_cast<float*>(st + out_off + out_scores_off), reinterpret_cast<int64_t*>(st + out_off + out_ids_off),
-                    reinterpret_cast<int32_t*>(st + out_off + out_counts_off), s, nullptr, index_dev, words, st + meta_off, &m);
-    if (e) return e;
+    float* ts = reinterpret_cast<float*>(st + out_off + out_scores_off);
+    int64_t* ti = reinterpret_cast<int64_t*>(st + out_off + out_ids_off);
+    int32_t* tc = reinterpret_cast<int32_t*>(st + out_off + out_counts_off);
+    // Small unmasked calls repeat with the same shapes (interactive queries): the second call of a shape is captured into
+    // a CUDA graph -- pack -> score -> top-k become ONE launch, the third call onwards replays it.  Everything the kernels
+    // read or write sits at fixed addresses (mapped staging block, handle scratch); h->generation changes when any moves.
+    b200ms::HostGraph* hg = nullptr;  // NOLINT
+    if (h->host_graph && !allow_dev) {
+      uint64_t key = 1469598103934665603ull;
+      auto mix = [&](uint64_t v) { key = (key ^ v) * 1099511628211ull; };
+      mix(uint64_t(n_q));
+      mix(uint64_t(k));
+      for (int i = 0; i < n_q; ++i) mix(uint64_t(uint32_t(q_lens[i])));
+      mix(uint64_t(id_base));
+      uint32_t fb;
+      memcpy(&fb, &score_scale, 4);
+      mix(fb);
+      memcpy(&fb, &i8_q_scale, 4);
+      mix(fb);
+      for (auto& g2 : h->host_graphs)
+        if (g2.key == key) hg = &g2;
+      if (!hg) {
+        if (h->host_graphs.size() >= 16) {  // evict the least recently used shape
+          size_t lru = 0;
+          for (size_t i = 1; i < h->host_graphs.size(); ++i)
+            if (h->host_graphs[i].last_use < h->host_graphs[lru].last_use) lru = i;
+          if (h->host_graphs[lru].exec) cudaGraphExecDestroy(h->host_graphs[lru].exec);
+          h->host_graphs.erase(h->host_graphs.begin() + long(lru));
+        }
+        h->host_graphs.emplace_back();
+        hg = &h->host_graphs.back();
+        hg->key = key;
+      }
+      hg->last_use = ++h->graph_clock;
+      if (hg->exec && hg->generation != h->generation) {  // a buffer moved / corpus or option changed: start over
+        cudaGraphExecDestroy(hg->exec);
+        hg->exec = nullptr;
+        hg->seen = 0;
+      }
+    }
+    if (hg && hg->exec) {
+      if (int e2 = check_cuda(h, cudaGraphLaunch(hg->exec, s), "search_host: graph launch")) return e2;
+      h->launches += hg->launches;
+    } else if (hg && hg->seen >= 1) {
+      const uint64_t gen0 = h->generation;
+      const int64_t l0 = h->launches;
+      if (int e2 = check_cuda(h, cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal), "search_host: begin capture")) return e2;
+      h->capturing = true;
+      e = search_core(h, st + q_off, B200MS_F32, q_lens, n_q, k, nullptr, i8_q_scale, score_scale, id_base, ts, ti, tc, s, nullptr,
+                      nullptr, words, st + meta_off, &m);
+      h->capturing = false;
+      cudaGraph_t graph = nullptr;
+      const cudaError_t ce = cudaStreamEndCapture(s, &graph);
+      if (e || ce != cudaSuccess || !graph || gen0 != h->generation) {
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        hg->seen = -1000000;  // this shape does not capture: plain launches from now on
+        e = search_core(h, st + q_off, B200MS_F32, q_lens, n_q, k, nullptr, i8_q_scale, score_scale, id_base, ts, ti, tc, s,
+                        nullptr, nullptr, words, st + meta_off, &m);
+        if (e) return e;
+      } else {
+        const cudaError_t ie = cudaGraphInstantiate(&hg->exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ie != cudaSuccess) {
+          cudaGetLastError();
+          hg->exec = nullptr;
+          hg->seen = -1000000;
+          e = search_core(h, st + q_off, B200MS_F32, q_lens, n_q, k, nullptr, i8_q_scale, score_scale, id_base, ts, ti, tc, s,
+                          nullptr, nullptr, words, st + meta_off, &m);
+          if (e) return e;
+        } else {
+          hg->generation = h->generation;
+          hg->launches = int(h->launches - l0);
+          if (int e2 = check_cuda(h, cudaGraphLaunch(hg->exec, s), "search_host: graph launch")) return e2;
+        }
+      }
+    } else {
+      if (hg) hg->seen++;
+      e = search_core(h, st + q_off, B200MS_F32, q_lens, n_q, k, allow_dev, i8_q_scale, score_scale, id_base, ts, ti, tc, s,
+                      nullptr, index_dev, words, st + meta_off, &m);
+      if (e) return e;
+    }
   } else {
     if (int e2 = reserve(h, h->q_raw, q_bytes ? q_bytes : 512)) return e2;
     if (int e2 = reserve(h, h->out_all, out_bytes)) return e2;

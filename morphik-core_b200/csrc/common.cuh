@@ -5,6 +5,7 @@
 #include <stdint.h>
 
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/b200ms.h"
@@ -108,7 +109,25 @@ struct b200ms {
   int pair_cta = 2;   // CTA-pair kernels (cta_group::2, maxsim_umma_pair.cu): 0 off, 1 for passes of >= 3 query tiles, 2 (default) also for 2 tiles
   int pair_clusters = -1;  // co-resident CTA pairs the device reports for the pair kernel (-1: not queried yet)
   int zero_pad_batch = 0;  // > 0: reproduce score_multi_vector's zero-padding quirk with this batch size (128 upstream)
-  CUtensorMap tmap_q;  // rebuilt per score call
+  CUtensorMap tmap_q;  // query tiles; re-encoded only when (pointer, dtype, rows) change
+  const void* tmap_q_base = nullptr;
+  int tmap_q_dtype = -1;
+  int64_t tmap_q_rows = -1;
+  // CUDA graphs of the small zero-copy host search (pack -> score -> top-k): key -> executable graph
+  struct HostGraph {
+    uint64_t key = 0;
+    uint64_t generation = 0;
+    cudaGraphExec_t exec = nullptr;
+    int launches = 0;
+    int seen = 0;  // uses of this key so far; the graph is captured on the second one (buffers are warm by then)
+    uint64_t last_use = 0;
+  };
+  std::vector<HostGraph> host_graphs;
+  uint64_t generation = 0;   // bumped whenever a scratch buffer moves, the corpus is re-attached or an option changes
+  uint64_t graph_clock = 0;
+  int host_graph = 1;        // option "host_graph": replay small unmasked host searches as one CUDA graph
+  bool capturing = false;    // inside stream capture: no event timing, no allocation
+  std::unordered_map<const void*, int> smem_attr;  // kernels whose MaxDynamicSharedMemorySize is already raised (this device)
 };
 
 namespace bms {
@@ -118,6 +137,8 @@ int check_cuda(b200ms_t* h, cudaError_t e, const char* what);
 int reserve(b200ms_t* h, DeviceBuf& b, size_t bytes);
 int upload(b200ms_t* h, DeviceBuf& b, const void* src, size_t bytes, cudaStream_t s);
 int reserve_pinned(b200ms_t* h, PinnedBuf& b, size_t bytes);
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (handle, kernel): it is a driver call on every launch otherwise
+int ensure_smem(b200ms_t* h, const void* kernel, int smem, const char* what);
 int make_tmap_rows(b200ms_t* h, CUtensorMap* out, const void* base, int dtype, int64_t n_rows, int box_rows,
                    int64_t row_bytes = 0);
 void comm_teardown(b200ms_t* h);

@@ -435,8 +435,7 @@ static int launch_fde_scan_simt(b200ms_t* h, const void* F, const float* inv_nor
                                 float* scores, int64_t ld, cudaStream_t s) {
   const int nq_res = n_q < kFdeQ ? n_q : kFdeQ;  // queries resident per launch
   const size_t smem = size_t(nq_res) * h->fde_dim * sizeof(float);
-  if (int e = check_cuda(h, cudaFuncSetAttribute(fde_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)),
-                         "cudaFuncSetAttribute(fde_scan)"))
+  if (int e = ensure_smem(h, reinterpret_cast<const void*>(fde_scan_kernel), int(smem), "cudaFuncSetAttribute(fde_scan)"))
     return e;
   int per_sm = int((220 * 1024) / (smem + 1024));  // CTAs per SM by shared memory (40 KB per resident query)
   if (per_sm < 1) per_sm = 1;
@@ -478,8 +477,7 @@ int launch_fde_scan(b200ms_t* h, const void* F, const float* inv_norm, int64_t n
     int stages = int((232448u - 1024u - 1024u) / stage_bytes);
     if (stages > 12) stages = 12;
     const uint32_t smem = 1024 + uint32_t(stages) * stage_bytes + 1024;
-    if (int e = check_cuda(h, cudaFuncSetAttribute(fde_scan_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)),
-                           "cudaFuncSetAttribute(fde_scan_umma)"))
+    if (int e = ensure_smem(h, reinterpret_cast<const void*>(fde_scan_umma_kernel), int(smem), "cudaFuncSetAttribute(fde_scan_umma)"))
       return e;
     const int64_t n_tiles = (n_pages + 127) / 128;
     const int grid = int(n_tiles < h->num_sms ? n_tiles : h->num_sms);

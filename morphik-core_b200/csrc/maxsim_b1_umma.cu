@@ -415,8 +415,7 @@ static int launch_b1_umma_one(b200ms_t* h, const CUtensorMap& tq, const int32_t*
   if (stages > 8) stages = 8;
   const uint32_t smem = 1024 + NM * kBTileBytes + uint32_t(stages) * kBTileBytes + 2048;
   auto kern = maxsim_b1_umma_kernel<NM, SPLIT4>;
-  if (int e = check_cuda(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)),
-                         "cudaFuncSetAttribute(maxsim_b1_umma)"))
+  if (int e = ensure_smem(h, reinterpret_cast<const void*>(kern), int(smem), "cudaFuncSetAttribute(maxsim_b1_umma)"))
     return e;
   int grid = h->max_ctas > 0 ? h->max_ctas : h->num_sms;
   if (grid > c.n_units) grid = c.n_units;
@@ -443,9 +442,11 @@ int launch_score_b1_umma(b200ms_t* h, const void* q_bits, const int32_t* group_n
   if (int e = check_cuda(h, cudaGetLastError(), "launch b1_query_expand")) return e;
   const int n_mtiles = n_groups_padded / 4;
   if (n_groups_real == 1) {  // single 32-token group: replicated-query form, 32-row TMA boxes
+    h->tmap_q_base = nullptr;  // this path re-encodes the shared descriptor with its own box shape
     if (int e = make_tmap_rows(h, &h->tmap_q, q_i8, B200MS_I8, n_rows, 32)) return e;
     return launch_b1_umma_one<1, true>(h, h->tmap_q, tok_const, 0, n_groups_real, group_scores, ld, s);
   }
+  h->tmap_q_base = nullptr;
   if (int e = make_tmap_rows(h, &h->tmap_q, q_i8, B200MS_I8, n_rows, kTileM)) return e;
   for (int base = 0; base < n_mtiles;) {
     const int rem = n_mtiles - base;

@@ -466,8 +466,7 @@ static int launch_w4(b200ms_t* h, const UnitPlan& up, const CUtensorMap& tq, int
   if (stages < 2) return set_error(h, B200MS_EINVAL, "maxsim_umma_w4: not enough shared memory for 2 stages");
   const uint32_t smem = 1024 + NM * K::kTileBytes + uint32_t(stages) * K::kTileBytes + kBarrierBytes;
   auto kern = maxsim_umma_w4_kernel<KIND, NM>;
-  if (int e = check_cuda(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)),
-                         "cudaFuncSetAttribute(maxsim_umma_w4)"))
+  if (int e = ensure_smem(h, reinterpret_cast<const void*>(kern), int(smem), "cudaFuncSetAttribute(maxsim_umma_w4)"))
     return e;
   int grid = h->max_ctas > 0 ? h->max_ctas : h->num_sms;
   if (grid > up.n_units) grid = up.n_units;
@@ -490,8 +489,7 @@ static int launch_one(b200ms_t* h, const UnitPlan& up, const CUtensorMap& tq, in
   if (stages > 8) stages = 8;
   const uint32_t smem = 1024 + NM * K::kTileBytes + uint32_t(stages) * K::kTileBytes + kBarrierBytes;
   auto kern = maxsim_umma_kernel<KIND, NM>;
-  if (int e = check_cuda(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)),
-                         "cudaFuncSetAttribute(maxsim_umma)"))
+  if (int e = ensure_smem(h, reinterpret_cast<const void*>(kern), int(smem), "cudaFuncSetAttribute(maxsim_umma)"))
     return e;
   int grid = h->max_ctas > 0 ? h->max_ctas : h->num_sms;
   if (grid > up.n_units) grid = up.n_units;
@@ -568,7 +566,12 @@ int launch_score_umma(b200ms_t* h, const UnitPlan* plan, const void* q_packed, i
   const int n_groups_padded = (n_groups_real + 3) & ~3;
   const int n_mtiles = n_groups_padded / 4;
   const int n_q_rows = n_groups_padded * kGroup;
-  if (int e = make_tmap_rows(h, &h->tmap_q, q_packed, c.dtype, int64_t(n_q_rows), kTileM)) return e;
+  if (h->tmap_q_base != q_packed || h->tmap_q_dtype != c.dtype || h->tmap_q_rows != n_q_rows) {
+    if (int e = make_tmap_rows(h, &h->tmap_q, q_packed, c.dtype, int64_t(n_q_rows), kTileM)) return e;
+    h->tmap_q_base = q_packed;
+    h->tmap_q_dtype = c.dtype;
+    h->tmap_q_rows = n_q_rows;
+  }
   if (m_tile_hi >= 0) {  // one explicit tile range: the single-tile kernel per tile (candidate lists are short)
     for (int m = m_tile_lo; m < m_tile_hi && m < n_mtiles; ++m) {
       int e;

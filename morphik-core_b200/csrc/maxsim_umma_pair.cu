@@ -535,8 +535,7 @@ static int launch_pair(b200ms_t* h, const UnitPlan& up, const CUtensorMap& tq, i
   if (stages < 2) return set_error(h, B200MS_EINVAL, "maxsim_umma_pair: not enough shared memory for 2 stages");
   const uint32_t smem = 1024 + NM * K::kTileBytes + uint32_t(stages) * K::kTileBytes + kBarrierBytes;
   auto kern = maxsim_umma_pair_kernel<KIND, NM>;
-  if (int e = check_cuda(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)),
-                         "cudaFuncSetAttribute(maxsim_umma_pair)"))
+  if (int e = ensure_smem(h, reinterpret_cast<const void*>(kern), int(smem), "cudaFuncSetAttribute(maxsim_umma_pair)"))
     return e;
   if (up.n_units < 1) return B200MS_OK;
   int grid = (h->max_ctas > 0 ? h->max_ctas : h->num_sms) & ~1;  // whole pairs
@@ -571,8 +570,7 @@ static int launch_pair1(b200ms_t* h, const UnitPlan& up, const CUtensorMap& tq, 
   if (stages > 8) stages = 8;
   const uint32_t smem = 1024 + K::kTileBytes + uint32_t(stages) * K::kTileBytes + kBarrierBytes;
   auto kern = maxsim_umma_pair1_kernel<KIND>;
-  if (int e = check_cuda(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)),
-                         "cudaFuncSetAttribute(maxsim_umma_pair1)"))
+  if (int e = ensure_smem(h, reinterpret_cast<const void*>(kern), int(smem), "cudaFuncSetAttribute(maxsim_umma_pair1)"))
     return e;
   if (up.n_units < 1) return B200MS_OK;
   if (h->pair_clusters < 0) {

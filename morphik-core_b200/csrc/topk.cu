@@ -117,23 +117,43 @@ topk_kernel(const T* __restrict__ gs, int64_t n_pages, int64_t ld, const int32_t
       }
     }
     __syncthreads();
-    if (tid == 0) {
-      if (pass == 0) {
-        uint32_t t = 0;
-        for (int b = 0; b < 256; ++b) t += hist[b];
-        s_total = t;
-        s_need = t < uint32_t(k) ? t : uint32_t(k);
+    if (wid == 0) {
+      // Which bin holds the need-th largest key?  Lane l owns bins [8l, 8l+8); a suffix scan over the lanes (high bins
+      // first) replaces the serial 256-bin walk one thread used to do per pass (~4 us per pass: it dominated the latency of
+      // small searches, configs[0]).
+      uint32_t loc[8], sum = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        loc[j] = hist[8 * lane + j];
+        sum += loc[j];
       }
-      uint32_t rem = s_need, b = 255;
-      if (rem > 0) {
-        for (;; --b) {
-          if (hist[b] >= rem) break;
-          rem -= hist[b];
-          if (b == 0) break;
+      uint32_t suf = sum;  // inclusive suffix sum: keys in bins >= 8*lane
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_down_sync(0xffffffffu, suf, o);
+        if (lane + o < 32) suf += v;
+      }
+      const uint32_t tot = __shfl_sync(0xffffffffu, suf, 0);
+      const uint32_t want = pass == 0 ? (tot < uint32_t(k) ? tot : uint32_t(k)) : s_need;
+      const uint32_t above = suf - sum;  // keys in bins owned by higher lanes
+      if (pass == 0 && lane == 0) s_total = tot;
+      if (want == 0) {
+        if (lane == 0) {
+          s_prefix = prefix | (255u << shift);
+          s_need = 0;
         }
+      } else if (suf >= want && above < want) {  // exactly one lane
+        uint32_t rem = want - above;
+        int bsel = -1;
+#pragma unroll
+        for (int j = 7; j >= 0; --j) {
+          if (bsel < 0) {
+            if (loc[j] >= rem) bsel = j; else rem -= loc[j];
+          }
+        }
+        s_prefix = prefix | (uint32_t(8 * lane + bsel) << shift);
+        s_need = rem;  // how many keys inside that bin are still needed
       }
-      s_prefix = prefix | (b << shift);
-      s_need = rem;  // how many keys inside bin b are still needed
     }
     __syncthreads();
     prefix = s_prefix;
@@ -289,8 +309,7 @@ static int launch_merge_impl(b200ms_t* h, const float* cand_scores, const uint32
   while (n2 < m) n2 <<= 1;
   const size_t smem = size_t(n2) * (sizeof(int64_t) + sizeof(uint32_t));
   auto kern = merge_topk_kernel<T>;
-  if (int e = check_cuda(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)),
-                         "cudaFuncSetAttribute(merge_topk)"))
+  if (int e = ensure_smem(h, reinterpret_cast<const void*>(kern), int(smem), "cudaFuncSetAttribute(merge_topk)"))
     return e;
   kern<<<n_q, 1024, smem, s>>>(cand_scores, cand_keys, cand_ids, m, n2, k, scale, top_scores, top_ids, top_counts, gathered, kx,
                                rank_stride, scores_off);

@@ -627,3 +627,29 @@ def test_sharded_search_pipeline_world1_matches_search():
     o = (torch.empty((len(prev[0]), 8)), torch.empty((len(prev[0]), 8), dtype=torch.int64), torch.empty((len(prev[0]),), dtype=torch.int32))
     idx.sharded_search_host_end(t_prev, *o)
     assert np.array_equal(o[1].numpy(), prev[1][1]) and np.array_equal(o[2].numpy(), prev[1][2])
+
+
+@pytest.mark.parametrize("dtype", ["bf16", "binary"])
+def test_host_graph_replay_matches_plain_launches(dtype):
+    """Small unmasked host searches of a repeated shape are captured into a CUDA graph on their second call and replayed
+    afterwards; results equal the plain launches, and a corpus change / option change invalidates the graph."""
+    rng = np.random.default_rng(91)
+    pages = make_pages(rng, list(rng.integers(1, 300, size=150)))
+    a = MaxSimIndex(dtype=dtype); a.add_pages(pages)
+    b = MaxSimIndex(dtype=dtype); b.set_option("host_graph", 0); b.add_pages(pages)
+    qs = [[unit_rows(rng, 32)] for _ in range(6)] + [[unit_rows(rng, 20), unit_rows(rng, 32)] for _ in range(4)]
+    l0 = a.launch_count()
+    for q in qs:  # same shape repeatedly: warm, capture, replay, replay, ...
+        ra, rb = a.search_host(q, k=7), b.search_host(q, k=7)
+        assert all(np.array_equal(x, y) for x, y in zip(ra, rb))
+    assert a.launch_count() - l0 >= 3 * len(qs)  # replays are counted: pack + score + top-k per call
+    extra = make_pages(rng, [64, 200, 1])
+    a.add_pages(extra); b.add_pages(extra)  # corpus re-attached: the captured graph must not be replayed
+    for q in qs[:4]:
+        ra, rb = a.search_host(q, k=7), b.search_host(q, k=7)
+        assert all(np.array_equal(x, y) for x, y in zip(ra, rb))
+    if dtype == "bf16":
+        a.set_option("zero_pad_compat", 128); b.set_option("zero_pad_compat", 128)
+        for q in qs[:4]:
+            ra, rb = a.search_host(q, k=7), b.search_host(q, k=7)
+            assert all(np.array_equal(x, y) for x, y in zip(ra, rb))
