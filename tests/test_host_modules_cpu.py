@@ -63,3 +63,23 @@ def test_shard_header_round_trip_and_rejection(tmp_path):
     pages = shardfile.pages_from_bit_rows([[bytes([0b10100101] + [0] * 15)], []])
     assert pages[0].shape == (1, 128) and pages[0][0, :8].tolist() == [1, -1, 1, -1, -1, 1, -1, 1] and pages[1].shape == (0, 128)
     assert np.array_equal(orc.sign_pack_c(pages[0])[0], np.array([0b10100101] + [0] * 15, dtype=np.uint8))
+
+
+def test_store_journal_log_survives_a_torn_last_line(tmp_path):
+    """journal.log is append-only; a crash mid-append leaves a torn last line that replay must ignore (everything before it
+    was fsynced); sequence numbers continue after the last complete segment."""
+    d = tmp_path / "store"
+    j = shardfile.StoreJournal(str(d))
+    assert j.read_ops() == [] and j.seq == 0
+    j._append({"op": "segment", "seq": 1, "pages": 3})
+    j.log_delete("doc-a")
+    j._append({"op": "segment", "seq": 2, "pages": 1})
+    with open(d / "journal.log", "a") as f:
+        f.write('{"op": "segment", "seq": 3, "pa')  # torn
+    ops = shardfile.StoreJournal(str(d)).read_ops()
+    assert [o["op"] for o in ops] == ["segment", "delete", "segment"] and ops[1]["document_id"] == "doc-a"
+    assert shardfile.StoreJournal(str(d)).seq == 2
+    assert j.segment_files(2)[0].endswith("seg-000002.b2ms")
+    (d / "seg-000001.b2ms").write_bytes(b"x")
+    j.reset()
+    assert sorted(p.name for p in d.iterdir()) == [] and j.seq == 0
