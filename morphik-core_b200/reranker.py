@@ -8,6 +8,7 @@ query's multivector: "retrieve with any store, rerank with ColPali MaxSim on the
 """
 from __future__ import annotations
 
+import asyncio
 import threading
 from typing import List, Optional, Sequence, Union
 
@@ -48,7 +49,7 @@ class B200MaxSimReranker:
         (document_service.py:381-383)."""
         if not chunks:
             return []
-        scores = self._scores(query_embedding, [c.embedding for c in chunks])
+        scores = await asyncio.to_thread(self._scores, query_embedding, [c.embedding for c in chunks])  # GPU work off the loop
         order = sorted(range(len(chunks)), key=lambda i: (-scores[i], i))
         out = []
         for i in order:
@@ -62,5 +63,5 @@ class B200MaxSimReranker:
     async def compute_score(self, query_embedding, page_embedding: Union[np.ndarray, Sequence]) -> Union[float, List[float]]:
         """One page ([P,128]) -> float; a list of pages -> list of floats (mirrors BaseReranker.compute_score's two forms)."""
         if isinstance(page_embedding, (list, tuple)) and len(page_embedding) and np.ndim(page_embedding[0]) == 2:
-            return [float(s) for s in self._scores(query_embedding, page_embedding)]
-        return float(self._scores(query_embedding, [page_embedding])[0])
+            return [float(s) for s in await asyncio.to_thread(self._scores, query_embedding, page_embedding)]
+        return float((await asyncio.to_thread(self._scores, query_embedding, [page_embedding]))[0])
