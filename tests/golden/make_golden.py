@@ -87,6 +87,16 @@ def gen_float_maxsim():
     pd = [torch.from_numpy(unit_rows(rng, 96)).bfloat16().float() for _ in range(16)]
     sd = ColPaliProcessor.score_retrieval(None, [qd], pd, batch_size=128, output_dtype=torch.float32)
     out.update(d_q=qd.numpy(), d_pages=torch.stack(pd).numpy(), d_scores=sd.numpy())
+    # case E: the rerank call of FastMultiVectorStore.query_similar (fast_multivector_store.py:553-555): ONE query against the
+    # candidate pages in FIRST-STAGE ORDER, one 128-batch (<= 75 candidates) -> the padding quirk follows the candidate list
+    lens_e = [int(x) for x in rng.integers(3, 90, size=40)]
+    pe = [torch.from_numpy(np.abs(unit_rows(rng, n))).bfloat16().float() for n in lens_e]  # bf16-valued, all-positive
+    cand_e = rng.permutation(40)[:25]
+    qe = [torch.from_numpy(-np.abs(unit_rows(rng, 20))).bfloat16().float(), torch.from_numpy(unit_rows(rng, 32)).bfloat16().float()]
+    se = torch.stack([ColPaliProcessor.score_retrieval(None, [q], [pe[int(c)] for c in cand_e], batch_size=128,
+                                                       output_dtype=torch.float32)[0] for q in qe])
+    out.update(e_rows=torch.cat(pe).numpy(), e_lens=np.array(lens_e), e_cand=cand_e.astype(np.int64), e_q0=qe[0].numpy(),
+               e_q1=qe[1].numpy(), e_scores=se.numpy())
     np.savez_compressed(os.path.join(OUT, "float_maxsim.npz"), **out)
 
 

@@ -564,6 +564,28 @@ def test_zero_pad_compat_rerank_batches_candidates_like_the_reference():
         np.testing.assert_allclose(ts[row].cpu().numpy(), [w[order[j]] for j in exp], rtol=3e-5, atol=1e-6)
 
 
+def test_zero_pad_compat_rerank_matches_port_golden(golden_dir):
+    """Golden case E (produced by the transformers port of score_multi_vector): the reference's rerank call, candidates in
+    first-stage order -- b200ms_rerank_batch_device with zero_pad_compat=128 returns the port's scores and ranking."""
+    fm = np.load(os.path.join(golden_dir, "float_maxsim.npz"))
+    lens = fm["e_lens"].tolist()
+    off = orc.page_offsets(lens)
+    pages = [fm["e_rows"][off[i]:off[i + 1]] for i in range(len(lens))]
+    cand = fm["e_cand"]
+    idx = MaxSimIndex(dtype="bf16")  # inputs are bf16-valued: storage is lossless
+    idx.set_option("zero_pad_compat", 128)
+    idx.add_pages(pages)
+    qs = [fm["e_q0"], fm["e_q1"]]
+    ci = torch.from_numpy(np.stack([cand, cand])).cuda()
+    ts, ti, tc = idx.rerank_batch(torch.from_numpy(np.concatenate(qs)).cuda(), [len(q) for q in qs], ci, k=len(cand))
+    torch.cuda.synchronize()
+    for qi in range(2):
+        want = fm["e_scores"][qi]
+        order = sorted(range(len(cand)), key=lambda j: (-want[j], j))
+        assert ti[qi].cpu().tolist() == [int(cand[j]) for j in order]
+        np.testing.assert_allclose(ts[qi].cpu().numpy(), want[order], rtol=2e-5, atol=2e-5)
+
+
 # ------------------------------------------------------------------------------------------------ batched rerank (per-query lists)
 @pytest.mark.parametrize("dtype", ["bf16", "int8", "binary"])
 def test_rerank_batch_per_query_candidate_lists(dtype):

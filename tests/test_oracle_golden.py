@@ -134,6 +134,20 @@ def test_float_maxsim_zero_pad_quirk_matches_port(fm):
     assert clean[longest] == compat[longest]
 
 
+def test_float_maxsim_rerank_in_candidate_order_matches_port(fm):
+    """Case E: the reference's rerank call -- one query against its <= 75 candidates in first-stage order, one batch
+    (fast_multivector_store.py:553-555).  The oracle restricted to the candidate pages IN THAT ORDER reproduces the port."""
+    off = orc.page_offsets(fm["e_lens"])
+    cand = fm["e_cand"]
+    sub_rows = np.concatenate([fm["e_rows"][off[c]:off[c + 1]] for c in cand])
+    sub_off = orc.page_offsets([int(fm["e_lens"][c]) for c in cand])
+    for qi, q in enumerate((fm["e_q0"], fm["e_q1"])):
+        got = orc.float_maxsim_c(q, sub_rows, sub_off, zero_pad_compat=True, batch=128)
+        np.testing.assert_allclose(got, fm["e_scores"][qi], rtol=2e-6, atol=2e-6)
+    longest = max(int(fm["e_lens"][c]) for c in cand)
+    assert all((s == 0.0) == (int(fm["e_lens"][c]) < longest) for s, c in zip(fm["e_scores"][0], cand))
+
+
 def test_float_maxsim_bf16_valued_inputs(fm):
     rows = fm["d_pages"].reshape(-1, 128)
     off = orc.page_offsets([fm["d_pages"].shape[1]] * fm["d_pages"].shape[0])

@@ -6,6 +6,19 @@ set -u
 mode=${1:-quick}
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,memory.total --format=csv,noheader | head -2
+if [ "$mode" = sanit ]; then
+  # compute-sanitizer over the kernels that are new this round (fde_scan_umma, clamp / rerank_batch plumbing, gathered merge,
+  # CUDA-graph replay, fp8) -- results go to gpurun_out/sanitizer_r02.txt
+  : > gpurun_out/sanitizer_r02.txt
+  for tool in memcheck synccheck; do
+    timeout -s KILL 900 compute-sanitizer --tool $tool python -m pytest tests -m gpu -q -x -k "fde_scan_tensor_path and 17 or rerank_batch_per_query and bf16 or zero_pad_compat_rerank or sharded_search_pipeline_world1 or host_graph_replay and bf16 or fp8_matches_oracle and 13 or cta_pair_form_agrees and fp8 and 57" > gpurun_out/sanit_$tool.log 2>&1
+    echo "== $tool rc=$?" >> gpurun_out/sanitizer_r02.txt; grep -E "ERROR SUMMARY|passed|failed|error" gpurun_out/sanit_$tool.log | tail -5 >> gpurun_out/sanitizer_r02.txt
+  done
+  timeout -s KILL 600 compute-sanitizer --tool racecheck python __graft_entry__.py smoke > gpurun_out/sanit_race.log 2>&1
+  echo "== racecheck smoke rc=$?" >> gpurun_out/sanitizer_r02.txt; grep -E "RACECHECK SUMMARY|smoke" gpurun_out/sanit_race.log | tail -3 >> gpurun_out/sanitizer_r02.txt
+  cat gpurun_out/sanitizer_r02.txt
+  exit 0
+fi
 if [ "$mode" != prof ]; then
   x=""; [ "$mode" = quick ] && x="-x"
   timeout -s KILL 1800 python -m pytest tests -m gpu -q $x --durations=8 2>&1 | tail -40 > gpurun_out/pytest_gpu.txt; tail -12 gpurun_out/pytest_gpu.txt
