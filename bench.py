@@ -48,7 +48,7 @@ if ROOT not in sys.path:
 P_PATCH, DIM, T_TOK = 1024, 128, 32
 METRIC = "patch_vectors_per_sec_maxsim"
 UNIT = "patch-vectors/s"
-N_TOPICS, N_ANCHORS = 2048, 16
+N_TOPICS, N_ANCHORS = 256, 16
 
 
 def load_traffic():

@@ -51,13 +51,16 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// mbarrier.try_wait already suspends the thread for a hardware-bounded time per attempt; after a burst of failed attempts
-// back off with __nanosleep so that a long wait (a peer CTA's tail, a starved producer) stops stealing issue slots from the
-// warps that do the work.  -DB200MS_MBAR_TIMEOUT=<polls> turns a hang into a trap with the barrier address (debug builds).
+// mbarrier.try_wait suspends the thread for a hardware-bounded time per attempt, so the loop below is not a hot spin.  The
+// per-tile waits of the pipelines (a few hundred cycles) must stay pure polls: a first version that slept after 32 failed
+// polls cost the 128-byte-row single-query scans 25 % of their HBM rate (a 16 KB tile lasts ~190 ns; a 32 ns nap plus its
+// wake-up latency is not small against that).  Only a wait that has already lasted tens of microseconds -- a peer CTA's tail,
+// a stream that ran out of units -- backs off with __nanosleep so it stops taking issue slots from the warps that work.
+// -DB200MS_MBAR_TIMEOUT=<polls> turns a hang into a trap with the barrier address (debug builds).
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t polls = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++polls > 32u) __nanosleep(polls > 1024u ? 256u : 32u);
+    if (++polls > 4096u) __nanosleep(128u);
 #ifdef B200MS_MBAR_TIMEOUT
     if (polls > uint32_t(B200MS_MBAR_TIMEOUT)) {
       printf("b200ms: mbarrier wait timed out (block %d thread %d bar %p parity %u)\n", int(blockIdx.x), int(threadIdx.x),
