@@ -198,6 +198,9 @@ int b200ms_comm_world(const b200ms_t* h);
 int64_t b200ms_xchg_bytes(int n_q, int k);
 /* ncclBroadcast of a device buffer from `root` (e.g. the query rows of a batch) on `stream`. */
 int b200ms_bcast_device(b200ms_t* h, void* buf, int64_t bytes, int root, void* stream);
+/* ncclSend / ncclRecv of a device buffer to / from rank `peer` (e.g. ingest rows from the coordinating rank to the owner). */
+int b200ms_send_device(b200ms_t* h, const void* buf, int64_t bytes, int peer, void* stream);
+int b200ms_recv_device(b200ms_t* h, void* buf, int64_t bytes, int peer, void* stream);
 /* The one collective of the path: all-gather every rank's xchg block (nccl_comm NULL = the handle's communicator) and merge
  * the world*k candidates per query -> identical top-k on every rank (score DESC, id ASC).  world * k <= 8192. */
 int b200ms_allgather_topk(b200ms_t* h, void* nccl_comm, const void* xchg_local_dev, int n_q, int k, float* top_scores_dev,

@@ -82,6 +82,8 @@ def _load() -> ctypes.CDLL:
         "b200ms_xchg_bytes": (c_int64, [c_int, c_int]),
         "b200ms_bcast_device": (c_int, [vp, vp, c_int64, c_int, vp]),
         "b200ms_allgather_topk": (c_int, [vp, vp, vp, c_int, c_int, vp, vp, vp, vp]),
+        "b200ms_send_device": (c_int, [vp, vp, c_int64, c_int, vp]),
+        "b200ms_recv_device": (c_int, [vp, vp, c_int64, c_int, vp]),
         "b200ms_sharded_search_begin": (c_int64, [vp, vp, c_int, i32p, c_int, c_int, vp, c_int, vp, c_float, c_float, c_int64, vp,
                                         vp, vp, vp]),
         "b200ms_sharded_search_end": (c_int, [vp, c_int64, vp]),
@@ -117,6 +119,7 @@ EXPORTED = [
     "b200ms_comm_rank", "b200ms_comm_world", "b200ms_xchg_bytes", "b200ms_bcast_device", "b200ms_allgather_topk",
     "b200ms_sharded_search_begin", "b200ms_sharded_search_end", "b200ms_sharded_search_host_begin",
     "b200ms_sharded_search_host_end", "b200ms_fde_configure_ex", "b200ms_fde_encode_corpus",
+    "b200ms_send_device", "b200ms_recv_device",
 ]
 
 

@@ -67,11 +67,20 @@ int reserve_pinned(b200ms_t* h, PinnedBuf& b, size_t bytes) {
   return B200MS_OK;
 }
 
+// MaxDynamicSharedMemorySize is a property of the FUNCTION in the device's context, shared by every handle of the process:
+// it must only ever be raised.  (A per-handle cache let a second handle "set" a small value for the merge kernel and thereby
+// LOWER the limit a first handle relied on -- its next large merge then failed with cudaErrorInvalidValue.)  Launches that fit
+// the 48 KB default need no call at all.
 int ensure_smem(b200ms_t* h, const void* kernel, int smem, const char* what) {
-  auto it = h->smem_attr.find(kernel);
-  if (it != h->smem_attr.end() && it->second >= smem) return B200MS_OK;
+  if (smem <= 48 * 1024) return B200MS_OK;
+  static std::mutex mu;
+  static std::unordered_map<uint64_t, int> raised;  // (device, kernel) -> largest value set so far
+  const uint64_t key = (uint64_t(uint32_t(h ? h->device : 0)) << 56) ^ uint64_t(reinterpret_cast<uintptr_t>(kernel));
+  std::lock_guard<std::mutex> lk(mu);
+  auto it = raised.find(key);
+  if (it != raised.end() && it->second >= smem) return B200MS_OK;
   if (int e = check_cuda(h, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), what)) return e;
-  h->smem_attr[kernel] = smem;
+  raised[key] = smem;
   return B200MS_OK;
 }
 

@@ -36,6 +36,8 @@ struct NcclApi {
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   ncclResult_t (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Broadcast)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
   ncclResult_t (*GetVersion)(int*) = nullptr;
   std::string where;
@@ -65,6 +67,8 @@ static NcclApi& nccl_api() {
     api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(dlsym(lib, "ncclCommDestroy"));
     api.AllGather = reinterpret_cast<decltype(api.AllGather)>(dlsym(lib, "ncclAllGather"));
     api.Broadcast = reinterpret_cast<decltype(api.Broadcast)>(dlsym(lib, "ncclBroadcast"));
+    api.Send = reinterpret_cast<decltype(api.Send)>(dlsym(lib, "ncclSend"));
+    api.Recv = reinterpret_cast<decltype(api.Recv)>(dlsym(lib, "ncclRecv"));
     api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(dlsym(lib, "ncclGetErrorString"));
     api.GetVersion = reinterpret_cast<decltype(api.GetVersion)>(dlsym(lib, "ncclGetVersion"));
     api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllGather && api.Broadcast;
@@ -225,6 +229,31 @@ B200MS_API int b200ms_bcast_device(b200ms_t* h, void* buf, int64_t bytes, int ro
   DeviceGuard g(h->device);
   h->launches++;
   return check_nccl(h, nccl_api().Broadcast(buf, buf, size_t(bytes), kNcclChar, root, c->comm, static_cast<cudaStream_t>(stream)), "ncclBroadcast");
+}
+
+// Point-to-point over the handle's communicator: ingest rows travel from the coordinating rank to the OWNING rank only.
+B200MS_API int b200ms_send_device(b200ms_t* h, const void* buf, int64_t bytes, int peer, void* stream) {
+  if (!h) return B200MS_EINVAL;
+  Comm* c = h->comm;
+  if (!c || !c->comm) return set_error(h, B200MS_ESTATE, "send: call b200ms_comm_init first (world > 1)");
+  if (bytes < 0 || (bytes > 0 && !buf) || peer < 0 || peer >= c->world || peer == c->rank || !nccl_api().Send)
+    return set_error(h, B200MS_EINVAL, "send: bad arguments (or ncclSend unavailable)");
+  if (bytes == 0) return B200MS_OK;
+  DeviceGuard g(h->device);
+  h->launches++;
+  return check_nccl(h, nccl_api().Send(buf, size_t(bytes), kNcclChar, peer, c->comm, static_cast<cudaStream_t>(stream)), "ncclSend");
+}
+
+B200MS_API int b200ms_recv_device(b200ms_t* h, void* buf, int64_t bytes, int peer, void* stream) {
+  if (!h) return B200MS_EINVAL;
+  Comm* c = h->comm;
+  if (!c || !c->comm) return set_error(h, B200MS_ESTATE, "recv: call b200ms_comm_init first (world > 1)");
+  if (bytes < 0 || (bytes > 0 && !buf) || peer < 0 || peer >= c->world || peer == c->rank || !nccl_api().Recv)
+    return set_error(h, B200MS_EINVAL, "recv: bad arguments (or ncclRecv unavailable)");
+  if (bytes == 0) return B200MS_OK;
+  DeviceGuard g(h->device);
+  h->launches++;
+  return check_nccl(h, nccl_api().Recv(buf, size_t(bytes), kNcclChar, peer, c->comm, static_cast<cudaStream_t>(stream)), "ncclRecv");
 }
 
 B200MS_API int b200ms_allgather_topk(b200ms_t* h, void* nccl_comm, const void* xchg_local, int n_q, int k, float* top_scores,

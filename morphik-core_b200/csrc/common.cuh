@@ -127,7 +127,7 @@ struct b200ms {
   uint64_t graph_clock = 0;
   int host_graph = 1;        // option "host_graph": replay small unmasked host searches as one CUDA graph
   bool capturing = false;    // inside stream capture: no event timing, no allocation
-  std::unordered_map<const void*, int> smem_attr;  // kernels whose MaxDynamicSharedMemorySize is already raised (this device)
+
 };
 
 namespace bms {

@@ -571,6 +571,18 @@ class MaxSimIndex:
                          "b200ms_bcast_device")
         return t
 
+    def send(self, t: torch.Tensor, peer: int):
+        """ncclSend of a contiguous device tensor to rank `peer` over the handle's communicator (torch's current stream)."""
+        with torch.cuda.device(self.device):
+            self.h.check(nat.lib.b200ms_send_device(self.h.ptr, _vp(t), t.numel() * t.element_size(), int(peer), self._stream()),
+                         "b200ms_send_device")
+
+    def recv(self, t: torch.Tensor, peer: int):
+        with torch.cuda.device(self.device):
+            self.h.check(nat.lib.b200ms_recv_device(self.h.ptr, _vp(t), t.numel() * t.element_size(), int(peer), self._stream()),
+                         "b200ms_recv_device")
+        return t
+
     def allgather_topk(self, xchg: torch.Tensor, n_q: int, k: int, out=None):
         """The one collective of the path for a caller-made local list: xchg = uint8 device buffer in the exchange layout
         ([n_q*k int64 global ids][n_q*k float32 scores]) -> merged (scores, ids, counts), identical on every rank."""

@@ -136,17 +136,26 @@ class ShardedB200MultiVectorStore(QueryCoalescer, BaseVectorStore):
         return t
 
     def _rows_to_owner(self, rows: Optional[np.ndarray], n_rows: int, owner: int) -> Optional[torch.Tensor]:
-        """Ingest rows travel to the owner only (the other ranks never see them)."""
+        """Ingest rows travel to the owner only (the other ranks never see them): ncclSend / ncclRecv on the handle's own
+        communicator with the CUDA index, torch.distributed send / recv with an injected stand-in (CPU tests)."""
+        native = hasattr(self.index, "send")
         if self.rank == 0:
             t = torch.from_numpy(np.ascontiguousarray(rows, dtype=np.float32)).to(self.data_device)
             if owner != 0 and n_rows:
-                dist.send(t, dst=self._peer(owner), group=self.group)
+                if native:
+                    self.index.send(t, owner)
+                    torch.cuda.current_stream(self.data_device).synchronize()  # t dies with this frame
+                else:
+                    dist.send(t, dst=self._peer(owner), group=self.group)
             return t if owner == 0 else None
         if owner != self.rank:
             return None
         t = torch.empty((n_rows, 128), dtype=torch.float32, device=self.data_device)
         if n_rows:
-            dist.recv(t, src=self._src(), group=self.group)
+            if native:
+                self.index.recv(t, 0)
+            else:
+                dist.recv(t, src=self._src(), group=self.group)
         return t
 
     def _agree(self, err: Optional[BaseException]) -> None:

@@ -23,7 +23,15 @@ def _free_port():
         return s.getsockname()[1]
 
 
+def _watchdog(seconds=90):
+    import faulthandler
+    import sys
+
+    faulthandler.dump_traceback_later(seconds, exit=True, file=sys.stderr)  # a hung collective must not burn the GPU lease
+
+
 def _worker(rank, world, port, mode, result_dir):
+    _watchdog()
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
@@ -102,6 +110,7 @@ def test_sharded_search_world2_nccl(tmp_path, mode):
 def _store_worker(rank, world, port, result_dir):
     import asyncio
 
+    _watchdog()
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
@@ -171,6 +180,7 @@ def _store_worker(rank, world, port, result_dir):
 def _two_stage_store_worker(rank, world, port, result_dir):
     import asyncio
 
+    _watchdog()
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))

@@ -24,6 +24,10 @@ import torch  # noqa: E402
 import bench  # noqa: E402
 from morphik_core_b200.catalog import PageRecord  # noqa: E402
 
+import faulthandler  # noqa: E402
+
+faulthandler.dump_traceback_later(int(os.environ.get("B200MS_WATCHDOG_S", "400")), exit=True)  # never hang a GPU lease
+
 ap = argparse.ArgumentParser()
 ap.add_argument("--pages", type=int, default=65536, help="pages per GPU")
 ap.add_argument("--clients", type=int, default=16)
