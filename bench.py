@@ -985,6 +985,11 @@ def two_stage_leg(args, idx, packed, n_pages, topic_pages, anchors, sharded, wor
 
 
 def main():
+    import faulthandler
+
+    wd = int(os.environ.get("B200MS_WATCHDOG_S", "0"))
+    if wd > 0:  # multi-GPU runs under a lease: a hung collective dumps every thread's stack and exits instead of idling
+        faulthandler.dump_traceback_later(wd, exit=True)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)

@@ -185,8 +185,9 @@ int b200ms_rerank_batch_device(b200ms_t* h, const void* q_dev, int src_dtype, co
  *   rank 0: b200ms_comm_unique_id(id) -> ship the 128 bytes to every rank by any means (file, socket, MPI, torch) ->
  *   every rank: b200ms_comm_init(h, id, rank, world)      (collective; creates the handle's own communicator)
  *   or b200ms_comm_adopt(h, ncclComm_t, rank, world) to use a communicator the host already has.
- * Exchange layout of one rank's list ("xchg"): [n_q*k int64 global page ids][n_q*k float32 scores], b200ms_xchg_bytes(n_q,k)
- * bytes, unused entries id -1 / score -inf -- b200ms_search_device can write it in place (top_ids_dev = xchg,
+ * Exchange layout of one rank's list ("xchg"): [n_q*k int64 global page ids][n_q*k float32 scores] padded to a multiple of
+ * 16 bytes = b200ms_xchg_bytes(n_q,k) bytes (so that every rank's block of the gathered buffer is 8-byte aligned), unused
+ * entries id -1 / score -inf -- b200ms_search_device can write it in place (top_ids_dev = xchg,
  * top_scores_dev = xchg + n_q*k*8). */
 int b200ms_comm_available(void);
 int b200ms_comm_unique_id(uint8_t* id128);

@@ -34,6 +34,7 @@ struct NcclApi {
   ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
   ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*CommAbort)(ncclComm_t) = nullptr;
   ncclResult_t (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Broadcast)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
@@ -65,6 +66,7 @@ static NcclApi& nccl_api() {
     api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(dlsym(lib, "ncclGetUniqueId"));
     api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(dlsym(lib, "ncclCommInitRank"));
     api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(dlsym(lib, "ncclCommDestroy"));
+    api.CommAbort = reinterpret_cast<decltype(api.CommAbort)>(dlsym(lib, "ncclCommAbort"));
     api.AllGather = reinterpret_cast<decltype(api.AllGather)>(dlsym(lib, "ncclAllGather"));
     api.Broadcast = reinterpret_cast<decltype(api.Broadcast)>(dlsym(lib, "ncclBroadcast"));
     api.Send = reinterpret_cast<decltype(api.Send)>(dlsym(lib, "ncclSend"));
@@ -84,8 +86,9 @@ static int check_nccl(b200ms_t* h, ncclResult_t r, const char* what) {
 }
 
 // Exchange layout of one rank's top-k list (what the all-gather moves, and what launch_merge_gathered reads):
-//   [n_q*k int64 global page ids][n_q*k float32 scores]   = 12 * n_q * k bytes;  unused entries: id -1, score -inf.
-static inline size_t xchg_bytes(int n_q, int k) { return size_t(n_q) * size_t(k) * 12; }
+//   [n_q*k int64 global page ids][n_q*k float32 scores], padded to a multiple of 16 bytes so that every rank's block of the
+//   gathered buffer starts 8-byte aligned (n_q*k*12 alone is not: 1 query x 7 entries = 84 bytes);  unused entries: id -1, -inf.
+static inline size_t xchg_bytes(int n_q, int k) { return (size_t(n_q) * size_t(k) * 12 + 15) & ~size_t(15); }
 
 constexpr int kSlots = 2;
 
@@ -126,10 +129,20 @@ static int ensure_comm_state(b200ms_t* h) {
   return B200MS_OK;
 }
 
+// ncclCommDestroy waits for the peers' matching call (measured: rank 0 sat in it forever while rank 1 had simply dropped its
+// handle), which makes handle destruction a hidden collective.  Every operation this handle issued is complete by now (the
+// caller synchronised the device), so the communicator is released with ncclCommAbort, which is local.
+static void release_comm(Comm* c) {
+  if (!c->comm || !c->owned || !nccl_api().ok) return;
+  if (c->cstream) cudaStreamSynchronize(c->cstream);
+  if (nccl_api().CommAbort) nccl_api().CommAbort(c->comm); else nccl_api().CommDestroy(c->comm);
+  c->comm = nullptr;
+}
+
 void comm_teardown(b200ms_t* h) {
   Comm* c = h->comm;
   if (!c) return;
-  if (c->comm && c->owned && nccl_api().ok) nccl_api().CommDestroy(c->comm);
+  release_comm(c);
   for (int i = 0; i < kSlots; ++i) {
     DeviceBuf* bufs[] = {&c->xchg[i], &c->gath[i], &c->q_raw[i], &c->out_dev[i], &c->lcount[i]};
     for (DeviceBuf* b : bufs)
@@ -180,7 +193,7 @@ B200MS_API int b200ms_comm_init(b200ms_t* h, const uint8_t* id128, int rank, int
   DeviceGuard g(h->device);
   if (int e = ensure_comm_state(h)) return e;
   Comm* c = h->comm;
-  if (c->comm && c->owned) a.CommDestroy(c->comm);
+  release_comm(c);
   c->comm = nullptr;
   c->rank = rank;
   c->world = world;
@@ -200,7 +213,7 @@ B200MS_API int b200ms_comm_adopt(b200ms_t* h, void* nccl_comm, int rank, int wor
   DeviceGuard g(h->device);
   if (int e = ensure_comm_state(h)) return e;
   Comm* c = h->comm;
-  if (c->comm && c->owned) nccl_api().CommDestroy(c->comm);
+  release_comm(c);
   c->comm = static_cast<ncclComm_t>(nccl_comm);
   c->owned = false;
   c->rank = rank;

@@ -53,7 +53,8 @@ def plan_document_shards(doc_rows: Sequence[int], world: int, weights: Optional[
 
 # ---- the exchange layout (same bytes as include/b200ms.h "xchg"): [n_q*k int64 ids][n_q*k float32 scores]
 def exchange_bytes(n_q: int, k: int) -> int:
-    return int(n_q) * int(k) * 12
+    """= b200ms_xchg_bytes: 12 bytes per entry, padded to 16 so that every rank's block of the gathered buffer is aligned."""
+    return (int(n_q) * int(k) * 12 + 15) // 16 * 16
 
 
 def exchange_views(buf: torch.Tensor, n_q: int, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -69,7 +70,7 @@ def gathered_candidates(gathered: torch.Tensor, world: int, n_q: int, k: int) ->
     g = gathered.view(world, exchange_bytes(n_q, k))
     n = n_q * k
     ids = g[:, : n * 8].contiguous().view(torch.int64).view(world, n_q, k)
-    sc = g[:, n * 8:].contiguous().view(torch.float32).view(world, n_q, k)
+    sc = g[:, n * 8: n * 12].contiguous().view(torch.float32).view(world, n_q, k)
     return (ids.permute(1, 0, 2).reshape(n_q, world * k).contiguous(), sc.permute(1, 0, 2).reshape(n_q, world * k).contiguous())
 
 

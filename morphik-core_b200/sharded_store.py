@@ -305,6 +305,8 @@ class ShardedB200MultiVectorStore(QueryCoalescer, BaseVectorStore):
             payload = self._bcast_payload(None, hdr[4])
             try:
                 if self._execute(hdr, payload, None) == "stop":
+                    if hasattr(self.index, "close"):
+                        self.index.close()  # releases this rank's communicator alongside rank 0's close()
                     return
             except ShardedStoreError as e:
                 logger.error("sharded store command failed: %s", e)

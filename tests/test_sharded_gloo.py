@@ -42,6 +42,7 @@ def test_plan_document_shards_weighted_by_rank_speed():
 
 def test_exchange_layout_views_and_gather():
     """The local top-k is written IN PLACE into [n_q*k int64 ids][n_q*k f32 scores]; the gathered buffer is world such blocks."""
+    assert exchange_bytes(1, 7) == 96 and exchange_bytes(32, 10) == 3840  # padded to 16: every gathered block stays aligned
     n_q, k, world = 3, 4, 2
     ids = torch.arange(24, dtype=torch.int64).reshape(world, n_q, k)
     sc = torch.arange(24, dtype=torch.float32).reshape(world, n_q, k) * 0.5

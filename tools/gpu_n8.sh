@@ -1,12 +1,13 @@
 #!/bin/bash
 # 8-GPU run (gpurun --gpus 8): bench at N=8 (equal shards, all legs), N=8 with speed-proportional placement (headline only),
-# the sharded plugin under 32 concurrent callers, and the sharded two-stage store.
+# the sharded plugin under 32 concurrent callers, and the sharded two-stage store.  Every step is time-boxed and carries a
+# faulthandler watchdog (a hung collective dumps its stacks and exits: 8 GPUs idling on a lease is the expensive failure).
 set -u
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=index,name --format=csv,noheader | head -8
-run() { timeout -s KILL "$1" python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port "$2" "${@:3}"; }
-run 900 29521 bench.py --gpus 8 --steps ${STEPS:-60} --warmup 5 > gpurun_out/bench_n8.json 2> gpurun_out/bench_n8.err; echo "bench n8 rc=$? lines=$(wc -l < gpurun_out/bench_n8.json)"; tail -4 gpurun_out/bench_n8.err
-run 600 29522 bench.py --gpus 8 --steps ${STEPS:-60} --warmup 5 --placement speed --skip-legs > gpurun_out/bench_n8_speed.json 2> gpurun_out/bench_n8_speed.err; echo "bench n8 speed rc=$?"; tail -3 gpurun_out/bench_n8_speed.err
+run() { B200MS_WATCHDOG_S="$1" timeout -s KILL "$2" python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port "$3" "${@:4}"; }
+run 230 250 29521 bench.py --gpus 8 --steps ${STEPS:-60} --warmup 5 > gpurun_out/bench_n8.json 2> gpurun_out/bench_n8.err; echo "bench n8 rc=$? lines=$(wc -l < gpurun_out/bench_n8.json)"; grep -v "^\[W" gpurun_out/bench_n8.err | grep -i "error\|assert\|File \"/" | tail -6
+run 130 150 29522 bench.py --gpus 8 --steps ${STEPS:-60} --warmup 5 --placement speed --skip-legs > gpurun_out/bench_n8_speed.json 2> gpurun_out/bench_n8_speed.err; echo "bench n8 speed rc=$?"; grep -v "^\[W" gpurun_out/bench_n8_speed.err | grep -i "error\|assert" | tail -3
 python - <<'PY'
 import json
 for f in ('gpurun_out/bench_n8.json','gpurun_out/bench_n8_speed.json'):
@@ -18,5 +19,5 @@ for f in ('gpurun_out/bench_n8.json','gpurun_out/bench_n8_speed.json'):
         if d.get('config4_two_stage'): print('  two_stage', {k:v for k,v in d['config4_two_stage'].items() if k in ('p50_ms','p95_ms','stage_ms_p50','recall','error')})
     except Exception as e: print(f, 'parse failed', e)
 PY
-run 600 29523 tools/bench_concurrency.py --sharded --clients 32 --rounds 15 --pages 65536 > gpurun_out/conc_n8.json 2> gpurun_out/conc_n8.err; echo "concurrency n8 rc=$?"; tail -c 2000 gpurun_out/conc_n8.json; tail -3 gpurun_out/conc_n8.err
-run 600 29524 tools/bench_concurrency.py --sharded --clients 8 --rounds 15 --pages 65536 --fde-candidates 1000 > gpurun_out/conc_n8_two_stage.json 2> gpurun_out/conc_n8_two_stage.err; echo "two-stage concurrency n8 rc=$?"; tail -c 1500 gpurun_out/conc_n8_two_stage.json; tail -3 gpurun_out/conc_n8_two_stage.err
+run 110 125 29523 tools/bench_concurrency.py --sharded --clients 32 --rounds 15 --pages 65536 > gpurun_out/conc_n8.json 2> gpurun_out/conc_n8.err; echo "concurrency n8 rc=$?"; tail -c 2000 gpurun_out/conc_n8.json; grep -v "^\[W\|^$" gpurun_out/conc_n8.err | tail -4
+run 90 100 29524 tools/bench_concurrency.py --sharded --clients 8 --rounds 15 --pages 65536 --fde-candidates 1000 > gpurun_out/conc_n8_two_stage.json 2> gpurun_out/conc_n8_two_stage.err; echo "two-stage concurrency n8 rc=$?"; tail -c 1500 gpurun_out/conc_n8_two_stage.json; grep -v "^\[W\|^$" gpurun_out/conc_n8_two_stage.err | tail -4
