@@ -153,9 +153,10 @@ def make_topic_queries(n_q: int, anchors, seed: int = 99):
 def build_shard(n_pages: int, device, seed: int, q_host, planted_per_query: int = 10, topic_pages: int = 0, anchors=None):
     """[n_pages*1024, 128] bf16 unit-norm rows in a 1024-aligned buffer; a few pages per query get 64 noisy copies of the
     query's tokens so that the top-k is meaningful (SURVEY 8d 'Synthetic inputs').  The first `topic_pages` pages follow a
-    topic model instead of pure noise: page p has topic p % N_TOPICS and a noise level that grows with p // N_TOPICS, its
-    rows are anchors of the topic + noise -- MaxSim and FDE similarity to a topic query both fall with the noise level, so
-    'recall of the exhaustive top-k among the FDE candidates' is a graded, meaningful number."""
+    topic model instead of pure noise: page p has topic p % N_TOPICS, covers a random ~60 % of the topic's 16 anchors and has a
+    noise level that grows with p // N_TOPICS; half of its rows are covered anchors + noise, the rest background -- MaxSim and FDE
+    similarity to a topic query both depend on coverage and noise, so 'recall of the exhaustive top-k among the FDE candidates'
+    is a graded, non-trivial number."""
     import torch
 
     rows_total = n_pages * P_PATCH
@@ -175,11 +176,16 @@ def build_shard(n_pages: int, device, seed: int, q_host, planted_per_query: int 
             level = (pid // N_TOPICS).float() / max(1, (topic_pages + N_TOPICS - 1) // N_TOPICS)  # 0 .. <1
             sigma = (0.25 + 1.75 * level) / DIM ** 0.5  # per-page noise: graded relevance inside a topic
             a = anchors[topic]  # [nt, 16, 128]
-            base = a.repeat(1, P_PATCH // N_ANCHORS, 1).reshape(nt * P_PATCH, DIM)
-            # half of every page stays background noise (real pages are not all on topic)
-            on_topic = (torch.arange(P_PATCH, device=device) % 2 == 0).repeat(nt)
+            # row r of a page: odd rows are background noise (real pages are not all on topic); even rows carry anchor
+            # (r // 2) % 16 of the page's topic -- if the page COVERS that anchor (each page covers a random ~60 % of them),
+            # so relevance is graded two ways: how many of the query's tokens a page can answer, and how noisily
+            r_idx = torch.arange(P_PATCH, device=device)
+            anchor_of_row = (r_idx // 2) % N_ANCHORS
+            cover = torch.rand((nt, N_ANCHORS), generator=g, device=device) < 0.6
+            on_topic = ((r_idx % 2 == 0)[None, :] & cover[:, anchor_of_row]).reshape(nt * P_PATCH)
+            base = a[:, anchor_of_row, :].reshape(nt * P_PATCH, DIM)
             xt = x[: nt * P_PATCH]
-            xt.mul_(sigma.repeat_interleave(P_PATCH)[:, None] * on_topic[:, None] + (~on_topic)[:, None] * 1.0)
+            xt.mul_(torch.where(on_topic, sigma.repeat_interleave(P_PATCH), torch.ones((), device=device))[:, None])
             xt.add_(base * on_topic[:, None])
         rows[p0 * P_PATCH:(p0 + n) * P_PATCH] = torch.nn.functional.normalize(x, dim=1).to(torch.bfloat16)
         del x
