@@ -227,6 +227,56 @@ topk_kernel(const T* __restrict__ gs, int64_t n_pages, int64_t ld, const int32_t
   if (tid == 0 && !part_keys) top_counts[q] = int32_t(kk);
 }
 
+// ------------------------------------------------------------------------------------------ small inputs: rank by counting
+// n_pages <= 1024 (configs[0]'s 100 pages, every rerank of <= 1024 candidates): one key per thread, each thread counts the
+// keys that precede its own -- (key DESC, page ASC), the same total order as the radix path -- and writes itself at that
+// rank.  One pass, two barriers; the radix select's four histogram passes cost ~5 us on such inputs, this ~1 us.
+template <typename T>
+__global__ void __launch_bounds__(kTopkThreads)
+topk_small_kernel(const T* __restrict__ gs, int64_t n_pages, int64_t ld, const int32_t* __restrict__ group_offsets,
+                  const uint32_t* __restrict__ allow_base, int k, float scale, int64_t id_base, const int64_t* __restrict__ id_map,
+                  float* __restrict__ top_scores, int64_t* __restrict__ top_ids, int32_t* __restrict__ top_counts,
+                  const int32_t* __restrict__ mask_index, int64_t mask_stride, int64_t q_stride) {
+  __shared__ uint32_t s_key[kTopkThreads];
+  __shared__ uint8_t s_ok[kTopkThreads];
+  __shared__ uint32_t s_total;
+  const int q = blockIdx.x;
+  const uint32_t* allow = allow_base;
+  if (mask_index && allow_base) {
+    const int mi = __ldg(mask_index + q);
+    allow = mi >= 0 ? allow_base + int64_t(mi) * mask_stride : nullptr;
+  }
+  const int g0 = group_offsets[q], g1 = group_offsets[q + 1];
+  const int tid = threadIdx.x;
+  const int n = int(n_pages);
+  const int64_t p = int64_t(q) * q_stride + tid;
+  uint32_t key = 0;
+  const bool valid = tid < n && page_key(gs, ld, g0, g1, allow, p, &key);
+  s_key[tid] = key;
+  s_ok[tid] = valid ? 1 : 0;
+  if (tid == 0) s_total = 0;
+  __syncthreads();
+  uint32_t rank = 0;
+  if (valid) {
+    for (int j = 0; j < n; ++j) {
+      const uint32_t kj = s_key[j];
+      rank += (s_ok[j] && (kj > key || (kj == key && j < tid))) ? 1u : 0u;
+    }
+    atomicAdd(&s_total, 1u);
+  }
+  // unused output slots first, then the winners (disjoint slots: ranks are unique)
+  for (int i = tid; i < k; i += kTopkThreads) {
+    top_scores[int64_t(q) * k + i] = -CUDART_INF_F;
+    top_ids[int64_t(q) * k + i] = -1;
+  }
+  __syncthreads();
+  if (valid && rank < uint32_t(k)) {
+    top_scores[int64_t(q) * k + rank] = score_of_key(key, T(0)) * scale;
+    top_ids[int64_t(q) * k + rank] = id_map ? __ldg(id_map + p) : p + id_base;
+  }
+  if (tid == 0) top_counts[q] = int32_t(s_total < uint32_t(k) ? s_total : uint32_t(k));
+}
+
 // ------------------------------------------------------------------------------------------ merge of candidate lists
 __device__ __forceinline__ bool cand_before(uint32_t ka, int64_t ia, uint32_t kb, int64_t ib) {
   return ka > kb || (ka == kb && ia < ib);  // score DESC, id ASC; invalid entries carry key 0 / id INT64_MAX
@@ -322,6 +372,19 @@ int launch_topk(b200ms_t* h, const void* group_scores, int score_dtype, int64_t 
                 int64_t id_base, const int64_t* id_map, float* top_scores, int64_t* top_ids, int32_t* top_counts,
                 cudaStream_t s, const int32_t* mask_index, int64_t mask_stride, int64_t q_stride) {
   if (n_q <= 0) return B200MS_OK;
+  if (n_pages <= kTopkThreads) {  // small inputs (incl. every rerank of <= 1024 candidates): one counting pass
+    if (score_dtype == B200MS_F32) {
+      topk_small_kernel<float><<<n_q, kTopkThreads, 0, s>>>(static_cast<const float*>(group_scores), n_pages, ld, group_offsets_dev,
+                                                           allow_mask, k, scale, id_base, id_map, top_scores, top_ids, top_counts,
+                                                           mask_index, mask_stride, q_stride);
+    } else {
+      topk_small_kernel<int><<<n_q, kTopkThreads, 0, s>>>(static_cast<const int*>(group_scores), n_pages, ld, group_offsets_dev,
+                                                         allow_mask, k, scale, id_base, id_map, top_scores, top_ids, top_counts,
+                                                         mask_index, mask_stride, q_stride);
+    }
+    h->launches++;
+    return check_cuda(h, cudaGetLastError(), "launch topk_small");
+  }
   int n2 = 1;
   while (n2 < k) n2 <<= 1;
   const size_t smem = size_t(n2) * sizeof(uint64_t);
