@@ -211,6 +211,12 @@ def set_cpu_threads():
     want = int(os.environ.get("B200MS_CPU_THREADS", "0")) or max(1, (os.cpu_count() or 2) // 2)
     if torch.get_num_threads() != want:
         torch.set_num_threads(want)
+    try:  # the C oracle (OpenMP) reads OMP_NUM_THREADS=1 under torchrun too: lift it for the checker legs
+        import ctypes
+
+        ctypes.CDLL("libgomp.so.1").omp_set_num_threads(int(want))
+    except Exception:  # noqa: BLE001
+        pass
 
 
 def cpu_reference_rate(n_q: int, budget_s: float, seed: int = 1234, pages_np=None, q_np=None):
@@ -438,6 +444,7 @@ def oracle_topk_check(idx, packed_bf16, q_host, n_queries, k, n_pages=512):
 
     from oracle import maxsim_oracle as orc
 
+    set_cpu_threads()
     rows = packed_bf16[: n_pages * P_PATCH * 256].view(torch.bfloat16).view(-1, DIM).float().cpu().numpy()
     off = orc.page_offsets([P_PATCH] * n_pages)
     allowed = np.zeros(idx.n_pages, dtype=bool)
@@ -607,6 +614,7 @@ def run_gpu(args):
         if rank == 0:
             from oracle import maxsim_oracle as orc
 
+            set_cpu_threads()
             all_rows = torch.cat(gathered).float().cpu().numpy()
             off = orc.page_offsets([P_PATCH] * (S * world))
             same, err = 0, 0.0
