@@ -27,6 +27,9 @@ class NativeError(RuntimeError):
 
 
 def _load() -> ctypes.CDLL:
+    override = os.environ.get("B200MS_LIB")  # developer A/B aid (tools/build_variants.py): an explicit variant of the library
+    if override:
+        return _declare(ctypes.CDLL(override))
     if not os.path.exists(LIB_PATH):
         raise ImportError(
             f"{LIB_PATH} is missing: build it with `python __graft_entry__.py build` "
@@ -39,7 +42,10 @@ def _load() -> ctypes.CDLL:
             f"{LIB_PATH} does not match morphik-core_b200/csrc (source hash differs): rebuild it with "
             "`python __graft_entry__.py build`."
         )
-    lib = ctypes.CDLL(LIB_PATH)
+    return _declare(ctypes.CDLL(LIB_PATH))
+
+
+def _declare(lib: ctypes.CDLL) -> ctypes.CDLL:
     vp, i32p, i64p, u32p, f32p = c_void_p, POINTER(c_int32), POINTER(c_int64), POINTER(c_uint32), POINTER(c_float)
     sig = {
         "b200ms_version": (c_int, []),

@@ -72,15 +72,27 @@ int reserve_pinned(b200ms_t* h, PinnedBuf& b, size_t bytes) {
 // LOWER the limit a first handle relied on -- its next large merge then failed with cudaErrorInvalidValue.)  Launches that fit
 // the 48 KB default need no call at all.
 int ensure_smem(b200ms_t* h, const void* kernel, int smem, const char* what) {
-  if (smem <= 48 * 1024) return B200MS_OK;
+  if (smem <= 16 * 1024) return B200MS_OK;  // static + dynamic cannot pass the 48 KB default below this
+  struct Entry {
+    int static_bytes;
+    int raised;  // largest MaxDynamicSharedMemorySize set so far (0 = never set)
+  };
   static std::mutex mu;
-  static std::unordered_map<uint64_t, int> raised;  // (device, kernel) -> largest value set so far
+  static std::unordered_map<uint64_t, Entry> table;  // (device, kernel)
   const uint64_t key = (uint64_t(uint32_t(h ? h->device : 0)) << 56) ^ uint64_t(reinterpret_cast<uintptr_t>(kernel));
   std::lock_guard<std::mutex> lk(mu);
-  auto it = raised.find(key);
-  if (it != raised.end() && it->second >= smem) return B200MS_OK;
+  auto it = table.find(key);
+  if (it == table.end()) {
+    cudaFuncAttributes fa;
+    if (int e = check_cuda(h, cudaFuncGetAttributes(&fa, kernel), what)) return e;
+    it = table.emplace(key, Entry{int(fa.sharedSizeBytes), 0}).first;
+  }
+  Entry& en = it->second;
+  // the default limit (48 KB) covers the kernel's STATIC shared memory as well as the dynamic request
+  if (en.raised == 0 && smem + en.static_bytes <= 48 * 1024) return B200MS_OK;
+  if (en.raised >= smem) return B200MS_OK;
   if (int e = check_cuda(h, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), what)) return e;
-  raised[key] = smem;
+  en.raised = smem;
   return B200MS_OK;
 }
 

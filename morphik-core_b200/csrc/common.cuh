@@ -137,7 +137,8 @@ int check_cuda(b200ms_t* h, cudaError_t e, const char* what);
 int reserve(b200ms_t* h, DeviceBuf& b, size_t bytes);
 int upload(b200ms_t* h, DeviceBuf& b, const void* src, size_t bytes, cudaStream_t s);
 int reserve_pinned(b200ms_t* h, PinnedBuf& b, size_t bytes);
-// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (handle, kernel): it is a driver call on every launch otherwise
+// Raise cudaFuncAttributeMaxDynamicSharedMemorySize when static + dynamic shared memory passes the 48 KB default; process-global
+// raise-only table per (device, kernel) -- the attribute belongs to the function, not to the handle
 int ensure_smem(b200ms_t* h, const void* kernel, int smem, const char* what);
 int make_tmap_rows(b200ms_t* h, CUtensorMap* out, const void* base, int dtype, int64_t n_rows, int box_rows,
                    int64_t row_bytes = 0);

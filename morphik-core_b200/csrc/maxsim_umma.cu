@@ -190,8 +190,8 @@ maxsim_umma_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_c
           tc_fence_after();
           if (active) {
             const uint32_t taddr = lane_base + buf * kTileN;
-            uint32_t va[32], vb[32];
             Acc cm[4];
+            uint32_t va[32], vb[32];
             tmem_ld_32x32(taddr, va);
             tmem_ld_32x32(taddr + 32, vb);
             tmem_ld_wait();

@@ -49,7 +49,7 @@ __device__ __forceinline__ float chunk_max_f(const uint32_t (&v)[32]) {
   a = fmax3(a, __uint_as_float(v[30]), __uint_as_float(v[31]));
   return fmaxf(a, b);
 }
-__device__ __forceinline__ int chunk_max_i_exact(const uint32_t (&v)[32]) {
+__device__ __forceinline__ int chunk_max_i(const uint32_t (&v)[32]) {
   int a = int(v[0]), b = int(v[1]);
 #pragma unroll
   for (int i = 2; i < 30; i += 4) {
@@ -59,19 +59,10 @@ __device__ __forceinline__ int chunk_max_i_exact(const uint32_t (&v)[32]) {
   a = imax3(a, int(v[30]), int(v[31]));
   return max(a, b);
 }
-// int32 accumulators through the FLOAT min/max datapath (FMNMX3 issues at twice the rate of VIMNMX3, which was what kept
-// the int8 batch kernels' tensor pipe at 55 %, profiles/r01).  The bit pattern of a non-negative int32 below 0x7f800000,
-// read as an IEEE float, is a non-negative (sub)normal whose ordering equals the integer ordering, and max.f32 (no .ftz)
-// keeps subnormals.  Negative ints read as negative floats or as NaN patterns (0xff800001..0xffffffff): max.f32 drops a NaN
-// operand when the other one is a number, and negative floats lose against any non-negative one.  So whenever at least one of
-// the 32 values is >= 0 the float maximum IS the integer maximum, bit for bit; otherwise the result is a negative float or
-// the canonical NaN 0x7fffffff, both >= 0x7f800000 as unsigned -- detected, and the chunk is redone with integer compares.
-// |acc| <= 127*127*128 < 2^21, so the fast path's range condition always holds for MaxSim scores.
-__device__ __forceinline__ int chunk_max_i(const uint32_t (&v)[32]) {
-  const uint32_t r = __float_as_uint(chunk_max_f(v));
-  if (r >= 0x7f800000u) return chunk_max_i_exact(v);  // every value negative: rare (a token whose best patch dot is < 0)
-  return int(r);
-}
+// (Round 2 tried the int32 accumulators on the FLOAT min/max datapath -- bit patterns of non-negative ints below 0x7f800000 order
+// like floats, with an integer redo when the float maximum came back negative / NaN.  Exact, but it bought nothing in the batch
+// regime (TMEM-drain-bound, 6.16 vs 6.24 ms) and cost 37 % for ONE query, where a single warp's dependent max chain is the
+// critical path: 1.42 ms integer vs 1.95 ms float at 65 536 pages, profiles/r02/ab_epilogue_variants.jsonl.  Integer it is.)
 template <typename Acc>
 __device__ __forceinline__ Acc chunk_max(const uint32_t (&v)[32]) {
   if constexpr (std::is_same<Acc, float>::value) {
