@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIB_DIR, "libb200ms.so")
-SOURCES = ["api.cu", "maxsim_umma.cu", "maxsim_umma_pair.cu", "maxsim_b1.cu", "maxsim_b1_umma.cu", "pack.cu", "topk.cu", "fde.cu", "comm.cu"]
+SOURCES = ["api.cu", "maxsim_umma.cu", "maxsim_umma_pair.cu", "maxsim_rowm.cu", "maxsim_b1.cu", "maxsim_b1_umma.cu", "pack.cu", "topk.cu", "fde.cu", "comm.cu"]
 HEADERS = ["common.cuh", "ptx.cuh", "umma_tile.cuh", os.path.join("..", "..", "include", "b200ms.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -240,6 +240,7 @@ B200MS_API int b200ms_create(int device, b200ms_t** out) {
   h->num_sms = prop.multiProcessorCount;
   if (const char* e = getenv("B200MS_B1_TENSOR")) h->b1_tensor = atoi(e);
   if (const char* e = getenv("B200MS_PAIR_CTA")) h->pair_cta = atoi(e);
+  if (const char* e = getenv("B200MS_ROWM")) h->rowm = atoi(e) != 0;
   if (const char* e = getenv("B200MS_ZERO_COPY")) h->zero_copy = atoi(e);
   if (const char* e = getenv("B200MS_UNIT_ROWS")) { if (atoll(e) > 0) h->unit_rows = atoll(e); }
   if (int e = check_cuda(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking), "cudaStreamCreate")) {
@@ -326,6 +327,8 @@ B200MS_API int b200ms_set_option(b200ms_t* h, const char* name, int64_t value) {
     h->zero_pad_batch = int(value);
   } else if (n == "zero_copy" && value >= 0 && value <= 1) {
     h->zero_copy = int(value);
+  } else if (n == "rowm" && value >= 0 && value <= 1) {
+    h->rowm = int(value);
   } else if (n == "fde_gemm" && value >= 0 && value <= 1) {
     h->fde_gemm = int(value);
   } else if (n == "host_graph" && value >= 0 && value <= 1) {
@@ -537,12 +540,16 @@ static int score_impl(b200ms_t* h, const void* q_packed, int n_groups, const int
     // b1_tensor: 0 = POPC kernel, 1 = tcgen05 kernel, 2 (default) = measured crossover: one 32-token group is faster on the
     // POPC pipe (1.59 vs 2.49 ms / 65536 pages), two or more groups on the tensor cores (a 128-token tile costs the same
     // as one token there).  Rerank of a candidate list stays on the POPC kernel.
-    const bool tensor_path = !cs.ids && (h->b1_tensor == 1 || (h->b1_tensor == 2 && n_groups >= 2));
+    // A full scan of ONE group runs with the patch rows as the M operand and the expanded bits in TMEM (maxsim_rowm.cu).
+    const bool rowm_path = !cs.ids && h->rowm && h->b1_tensor != 0 && n_groups == 1;
+    const bool tensor_path = rowm_path || (!cs.ids && (h->b1_tensor == 1 || (h->b1_tensor == 2 && n_groups >= 2)));
     if ((tensor_path && c.has_empty) || cs.per_query)
       if (int e = check_cuda(h, cudaMemsetAsync(group_scores, 0, size_t(n_groups_padded) * size_t(ld) * 4, s), "score: memset")) return e;
     if (!h->capturing)
       if (int e = check_cuda(h, cudaEventRecord(h->ev0[slot], s), "score: event record")) return e;
-    if (tensor_path) {
+    if (rowm_path) {
+      if (int e = launch_score_rowm(h, q_packed, n_groups, ntok_dev, nullptr, group_scores, ld, s)) return e;
+    } else if (tensor_path) {
       if (int e = launch_score_b1_umma(h, q_packed, ntok_dev, n_groups, group_scores, ld, s)) return e;
     } else if (cs.per_query) {
       for (int q = 0; q < n_q; ++q) {
@@ -613,6 +620,9 @@ static int score_impl(b200ms_t* h, const void* q_packed, int n_groups, const int
       void* sc = static_cast<uint8_t*>(group_scores) + size_t(s0) * 4;
       if (int e = launch_score_umma(h, &sub, q_packed, n_groups, sc, ld, s, m, m + 1)) return e;
     }
+  } else if (!cs.ids && h->rowm && n_groups <= kRowmMaxGroups) {
+    // the lone query: patch rows as the M operand, four epilogue warps in parallel (maxsim_rowm.cu)
+    if (int e = launch_score_rowm(h, q_packed, n_groups, nullptr, plan.clamp_bits, group_scores, ld, s)) return e;
   } else {
     if (int e = launch_score_umma(h, &plan, q_packed, n_groups, group_scores, ld, s)) return e;
   }

@@ -16,6 +16,7 @@ constexpr int kDim = B200MS_DIM;
 constexpr int kGroup = B200MS_ROW_GROUP;  // 32 rows: padding granule of pages and queries ("chunk")
 constexpr int kTileN = 128;               // patch rows per MMA tile (4 chunks)
 constexpr int kTileM = 128;               // query rows per MMA tile (4 groups)
+constexpr int kRowmMaxGroups = 2;         // maxsim_rowm.cu (patch rows as the M operand): scans of <= 2 query groups
 
 struct DeviceBuf {  // grow-only device scratch
   void* p = nullptr;
@@ -113,6 +114,12 @@ struct b200ms {
   const void* tmap_q_base = nullptr;
   int tmap_q_dtype = -1;
   int64_t tmap_q_rows = -1;
+  CUtensorMap tmap_qn;  // the same query rows as a 32*NG-row box (maxsim_rowm.cu: the query is the N operand)
+  const void* tmap_qn_base = nullptr;
+  int tmap_qn_dtype = -1;
+  int64_t tmap_qn_rows = -1;
+  int tmap_qn_box = 0;
+  int rowm = 1;  // option "rowm": full scans of <= kRowmMaxGroups query groups run on maxsim_rowm_kernel (0: query-as-M kernels)
   // CUDA graphs of the small zero-copy host search (pack -> score -> top-k): key -> executable graph
   struct HostGraph {
     uint64_t key = 0;
@@ -162,6 +169,8 @@ int launch_clamp_slots(b200ms_t* h, const int64_t* cand_ids, int n_cand, int n_l
                        uint32_t* clamp_bits, cudaStream_t s);
 int launch_score_b1_umma(b200ms_t* h, const void* q_bits, const int32_t* group_ntok_dev, int n_groups_real,
                          void* group_scores, int64_t ld, cudaStream_t s);
+int launch_score_rowm(b200ms_t* h, const void* q_packed, int n_groups_real, const int32_t* ntok_dev, const uint32_t* clamp_bits,
+                      void* group_scores, int64_t ld, cudaStream_t s);
 int launch_cand_units(b200ms_t* h, const int64_t* cand_ids, int n_cand, int32_t* unit_start, int32_t* unit_end,
                       uint32_t* slot_mask, cudaStream_t s);
 int launch_hamming_batch(b200ms_t* h, const void* q, const void* cand, int64_t n, uint32_t* out, cudaStream_t s);

@@ -486,7 +486,7 @@ static int launch_one(b200ms_t* h, const UnitPlan& up, const CUtensorMap& tq, in
   const Corpus& c = h->corpus;
   const uint32_t avail = kSmemLimit - 1024 /*align*/ - kBarrierBytes - NM * K::kTileBytes;
   int stages = int(avail / K::kTileBytes);
-  if (stages > 8) stages = 8;
+  if (stages > 14) stages = 14;  // 16 KB tiles: 8 stages = 128 KB in flight left the one-byte scans latency-bound (full[16])
   const uint32_t smem = 1024 + NM * K::kTileBytes + uint32_t(stages) * K::kTileBytes + kBarrierBytes;
   auto kern = maxsim_umma_kernel<KIND, NM>;
   if (int e = ensure_smem(h, reinterpret_cast<const void*>(kern), int(smem), "cudaFuncSetAttribute(maxsim_umma)"))

@@ -178,6 +178,53 @@ def test_cta_pair_form_agrees(dtype, unit_rows_, n_pages):
             assert_close_rel(ga, oracle_float(queries, pages), 3e-5)
 
 
+@pytest.mark.parametrize("dtype", ["bf16", "int8", "fp8", "binary"])
+@pytest.mark.parametrize("unit_rows_,n_pages", [(400, 70), (64, 9), (4096, 70), (400, 1), (0, 400)])
+def test_rows_as_m_kernel_is_bit_identical_to_query_as_m(dtype, unit_rows_, n_pages):
+    """maxsim_rowm_kernel (lone query: patch rows = M operand, four epilogue warps, cross-warp page combine in shared memory)
+    against the query-as-M kernels it replaces for scans of <= 2 query groups: 1 and 2 groups, short last groups, pages of
+    1 .. 1030 rows (pages inside one chunk, pages crossing tiles and units), empty pages, one page only, more units than SMs."""
+    rng = np.random.default_rng(1234 + n_pages)
+    base = [1, 31, 32, 33, 0, 64, 127, 128, 129, 5, 700, 1030, 0, 2, 96, 255, 256, 257, 40, 1]
+    lens = (base + list(rng.integers(1, 300, size=400)))[:n_pages] if n_pages > 1 else [333]
+    if n_pages == 400:
+        lens = list(rng.integers(1, 1100, size=400))
+    pages = make_pages(rng, lens)
+    a = MaxSimIndex(dtype=dtype); a.set_option("rowm", 1)
+    b = MaxSimIndex(dtype=dtype); b.set_option("rowm", 0)
+    if dtype == "binary":
+        b.set_option("b1_tensor", 0)  # the POPC kernel: an independent formulation
+    for ix in (a, b):
+        if unit_rows_:
+            ix.set_option("unit_rows", unit_rows_)
+        ix.add_pages(pages)
+    for qs in ([unit_rows(rng, 32)], [unit_rows(rng, 7)], [-np.abs(unit_rows(rng, 20))], [unit_rows(rng, 64)],
+               [unit_rows(rng, 45)], [unit_rows(rng, 32), unit_rows(rng, 3)]):
+        ga, gb = a.score_matrix(qs), b.score_matrix(qs)
+        assert np.array_equal(ga, gb), (dtype, [len(q) for q in qs], np.abs(ga - gb).max(), np.argwhere(ga != gb)[:5])
+        ta, tb = a.search_host(qs, k=7), b.search_host(qs, k=7)
+        assert np.array_equal(ta[1], tb[1]) and np.array_equal(ta[0], tb[0])
+    if dtype == "bf16":
+        qs = [unit_rows(rng, 32), unit_rows(rng, 30)]
+        assert_close_rel(a.score_matrix(qs), oracle_float(qs, pages), 3e-5)
+        for ix in (a, b):
+            ix.set_option("zero_pad_compat", 16)
+        q1 = [-np.abs(unit_rows(rng, 20))]
+        assert np.array_equal(a.score_matrix(q1), b.score_matrix(q1))
+
+
+def test_rows_as_m_kernel_binary_matches_oracle_on_uniform_pages():
+    """1024-row pages (the BASELINE shape): every page spans 8 tiles and all four epilogue warps; exact integers."""
+    rng = np.random.default_rng(77)
+    lens = [1024] * 300
+    pages = make_pages(rng, lens)
+    idx = MaxSimIndex(dtype="binary"); idx.add_pages(pages)
+    q = [unit_rows(rng, 32)]
+    got = idx.score_matrix(q)
+    want, _ = orc.binary_maxsim_c(orc.sign_pack_c(q[0]), orc.sign_pack_c(np.concatenate(pages)), orc.page_offsets(lens))
+    assert np.array_equal(got[0], want)
+
+
 def test_cta_pair_form_large_and_topk():
     """Pair kernel on a corpus that gives every pair many units (persistent loop, stage ring wrap, dummy tail tiles)."""
     rng = np.random.default_rng(4242)

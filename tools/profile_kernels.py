@@ -50,7 +50,7 @@ if args.only == "bf16":
 elif args.only in ("int8", "fp8"):
     drive(bench.quantised_subshard(packed, args.pages, args.only, 0), [int(b) for b in args.bqs.split(",")])
 elif args.only == "binary":
-    drive(bench.quantised_subshard(packed, args.pages, "binary", 0), [8, 1])
+    drive(bench.quantised_subshard(packed, args.pages, "binary", 0), [int(b) for b in args.bqs.split(",")] if args.bqs != "32,1" else [8, 1])
 else:
     from morphik_core_b200.fde import TwoStageIndex
 
