@@ -274,6 +274,9 @@ int b200ms_set_tuning(b200ms_t* h, int64_t unit_rows, int max_ctas);
  *   "pair_cta"        CTA pairs with tcgen05 cta_group::2, M = N = 256: 0 = off, 1 = passes of >= 3 query tiles, 2 = also
  *                     exactly 2 tiles (default)
  *   "b1_tensor"       1 = score 1-bit corpora on tcgen05 with in-kernel bit expansion, 0 = POPC kernel, 2 = auto by group count
+ *   "rowm"            1 (default) = full scans of <= 2 query groups (<= 64 query tokens; sign-bit corpora: 1 group) run on
+ *                     maxsim_rowm_kernel: patch rows are the tcgen05 M operand, the query tokens N = 32 or 64, four lane-quadrant
+ *                     epilogue warps in parallel; 0 = the query-as-M kernels (same results bit for bit)
  *   "zero_pad_compat" N > 0: reproduce colpali_engine score_multi_vector's zero-padding quirk with batch size N (128 upstream,
  *                     processing_colpali.py:350-362): a page shorter than the longest page of its batch scores
  *                     sum_t max(max_r <q_t,d_r>, 0).  Rerank calls batch the candidates in first-stage order (exactly the

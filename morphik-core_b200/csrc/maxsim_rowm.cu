@@ -19,13 +19,22 @@
 //     table (atomicMax per token + a chunk counter per page; the warp that completes the page's chunk count sums the tokens
 //     and writes the score).  Pages are whole inside a CTA's unit, so no global atomics are needed.
 //
-// KIND 0 bf16, 1 int8, 2 fp8 e4m3: patch tiles arrive by TMA exactly as in maxsim_umma.cu.
-// KIND 3 sign bits: rows stay 16 B in HBM; a bulk-copy ring brings 2 KB raw tiles into shared memory and eight expander warps
-//   inflate them to {0,1} int8 in the SWIZZLE_128B K-major layout (two instructions per 4 elements: shift + mask -- the K
-//   order inside each 32-bit word is permuted, element 4m+i <- bit m+8i, and the query is expanded with the same permutation,
-//   which a dot product cannot see), then kind::i8 as in maxsim_b1_umma.cu:  128 - ham = (128 - popc(q)) + <q', d'>.
+// KIND 0 bf16, 1 int8, 2 fp8 e4m3: patch tiles arrive by TMA exactly as in maxsim_umma.cu (up to 14 stages: 16 KB tiles need
+//   > 128 KB in flight per SM), A and B from shared memory.
+// KIND 3 sign bits: rows stay 16 B in HBM.  A bulk-copy ring brings raw bits into shared memory (16 KB slots = 8 tiles, one
+//   request per contiguous run); eight expander warps -- two per TMEM lane quadrant, alternating tiles, one thread per patch row --
+//   turn 16 B of bits into 32 words of {0,1} bytes (shift + mask per word; the K order inside a 32-bit word is permuted,
+//   element 4m+i <- bit m+8i, and the query is expanded with the same permutation, which a dot product cannot see) and store
+//   them with ONE tcgen05.st straight into TMEM, where tcgen05.mma kind::i8 reads its A operand (no shared-memory store, no
+//   swizzle, no proxy fence).  128 - ham = (128 - popc(q)) + <q', d'> as in maxsim_b1_umma.cu.
+// Two epilogue warps per lane quadrant alternate tiles as well: every per-tile loop in this kernel is a serial chain inside a
+//   lone warp that pays full latency per instruction (ncu: ~10 cycles each), so the loops are kept short -- the MMA issuer and
+//   the expanders only count tiles, the epilogue does its page bookkeeping once per 8-tile block from two ballots (chunk ->
+//   page ids prefetched one block ahead; page extents come from the masks, not from page_start) and has a fast path for blocks
+//   that lie inside one page.
 // Results: bit-identical to the query-as-M kernels (integer kinds exact; float kinds take the same max and the same
-// lane-order warp sum).
+// lane-order warp sum).  Measured (65536 pages x 1024, one 32-token query, B200): bf16 2.37 ms = 7.25 TB/s (query-as-M: 2.50),
+// int8 / fp8 1.17-1.27 ms = 6.8-7.4 TB/s (1.47), sign bits 0.97 ms (POPC kernel 1.57); profiles/r02/README.md section 8.
 #include <climits>
 
 #include "common.cuh"
@@ -53,6 +62,22 @@ __device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_
 }
 __device__ __forceinline__ void mbar_expect_tx_only(uint64_t* bar, uint32_t bytes) {  // no arrival: more bytes for the current phase
   asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// mbarrier wait with a suspend-time hint: the thread sleeps inside the try_wait until the phase completes (or ~2 us pass) instead of
+// coming back every ~90 cycles.  In this kernel the pollers share their SM sub-partition's issue slots with the warps that
+// work (ncu: 1050 warp instructions per 128-row tile, 18 % of them polling, issue-bound), so fewer polls is throughput.
+__device__ __forceinline__ void rm_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity), "r"(2000u)
+        : "memory");
+  } while (!ok);
 }
 __device__ __forceinline__ uint2 ld_shared_v2(uint32_t addr) {
   uint2 v;
@@ -188,9 +213,19 @@ struct RmPages {
   __device__ __forceinline__ static int load(const int32_t* chunk_page, int base, int limit, int lane) {
     return base + lane < limit ? __ldg(chunk_page + base + lane) : -1;
   }
-  __device__ __forceinline__ void begin_block(const RmTiles& it, const int32_t* chunk_page, int n_units, int lane) {
+  // Two steps on purpose.  take(): cur <- the block loaded one block ago (a synchronous reload only if the lookahead guessed
+  // wrong).  prefetch(): issue the next block's load AFTER every use of cur in the block setup -- ptxas shares scoreboards, and
+  // with the load issued first the first consumer of cur waited for the NEW load as well (a DRAM round trip per block, ncu).
+  __device__ __forceinline__ void take(const RmTiles& it, const int32_t* chunk_page, int lane) {
     const int base = it.c0 + 4 * it.t;  // it.t % 8 == 0
-    cur = (nxt_base == base) ? nxt : load(chunk_page, base, it.c1, lane);
+    if (nxt_base != base) {
+      nxt = load(chunk_page, base, it.c1, lane);
+      nxt_base = base;
+    }
+    cur = nxt;
+  }
+  __device__ __forceinline__ void prefetch(const RmTiles& it, const int32_t* chunk_page, int n_units, int lane) {
+    const int base = it.c0 + 4 * it.t;
     if (it.t + 8 < it.n_tiles) {
       nxt_base = base + 32;
       nxt = load(chunk_page, nxt_base, it.c1, lane);
@@ -342,7 +377,7 @@ maxsim_rowm_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_c
         };
         for (; it.valid(n_units); it.next(unit_start, unit_end, n_units)) {
           const int64_t row0 = int64_t(it.chunk0()) * kGroup;
-          if (in_group == 0) mbar_wait(&rempty[rg], gphase ^ 1);
+          if (in_group == 0) rm_wait(&rempty[rg], gphase ^ 1);
           if (run_tiles > 0 && row0 == run_row0 + int64_t(run_tiles) * 128) {
             ++run_tiles;
           } else {
@@ -369,7 +404,7 @@ maxsim_rowm_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_c
         int stage = 0;
         uint32_t phase = 0;
         for (; it.valid(n_units); it.next(unit_start, unit_end, n_units)) {
-          mbar_wait(&empty[stage], phase ^ 1);
+          rm_wait(&empty[stage], phase ^ 1);
           mbar_expect_tx(&full[stage], K::kTileBytes);
           uint8_t* dst = smem_st + size_t(stage) * K::kTileBytes;
           const int row0 = it.chunk0() * kGroup;
@@ -388,15 +423,15 @@ maxsim_rowm_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_c
     constexpr uint32_t idesc = umma_idesc(T::kMmaKind, kTileN, int(kAccCols));
     constexpr uint32_t kTileDesc = K::kTileBytes >> 4;
     if (elect_one()) {  // one thread runs the whole loop: no per-tile elect / warp sync
-      mbar_wait(qfull, 0);
+      rm_wait(qfull, 0);
       tc_fence_after();
       const uint64_t a_desc0 = umma_desc_kmajor_sw128(smem_u32(smem_st));
       const uint64_t b_desc0 = umma_desc_kmajor_sw128(smem_u32(smem_q));
       uint32_t stage = 0, phase = 0;
       for (uint32_t seq = 0; seq < total_tiles; ++seq) {
         const uint32_t buf = seq & (kAcc - 1);
-        mbar_wait(&full[stage], phase);
-        mbar_wait(&tempty[buf], ((seq / kAcc) & 1) ^ 1);
+        rm_wait(&full[stage], phase);
+        rm_wait(&tempty[buf], ((seq / kAcc) & 1) ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + buf * kAccCols;
 #pragma unroll
@@ -432,8 +467,11 @@ maxsim_rowm_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_c
 #pragma unroll
     for (int g = 0; g < NG; ++g) cn[g] = (KIND == 3 && g < n_groups_real) ? __ldg(tok_const + g * 32 + lane) : 0;
     int cp = -1, cord = 0, ccount = 0;  // page this warp is accumulating, its ordinal in the CTA's page sequence, chunks so far
-    int64_t ps_lo = 0, ps_hi = 0;       // page_start[cp], page_start[cp + 1]
-    int last_pg = -1, ord_base = 0;     // page of the last chunk of the previous block, page changes before this block
+    // Positions in the CTA's chunk sequence (every warp sees every block's masks, so all of this is register arithmetic -- a
+    // page_start load per page put a DRAM round trip on the scoreboards the tile loop waits on):
+    int g_base = 0, last_change_g = -1;  // index of this block's chunk 0; index of the last page change before this block
+    int cp_start_g = 0, cp_end_g = -1;   // [first chunk, one past the last chunk) of page cp; end < 0: not seen yet
+    int last_pg = -1, ord_base = 0;      // page of the last chunk of the previous block, page changes before this block
     uint32_t cmask = 0, vmask = 0;      // this block: chunk i starts a new page / chunk i exists
     uint32_t seq = 0;
 
@@ -449,7 +487,7 @@ maxsim_rowm_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_c
       int old = 0;
       if (lane == 0) old = smem_atom_add(cnt_s + slot * 4u, ccount);
       old = __shfl_sync(0xffffffffu, old, 0);
-      const int total = int((ps_hi - ps_lo) >> 5);  // loaded when the page was adopted: no DRAM round trip inside the flush
+      const int total = cp_end_g - cp_start_g;  // chunks of page cp
       if (old + ccount == total) {  // this warp brought the page's last chunks: every warp's maxima are in the table
         fence_cta();
 #pragma unroll
@@ -466,13 +504,15 @@ maxsim_rowm_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_c
       }
     };
 
-    auto adopt = [&](int pg, int ordinal) {  // this warp's next chunk belongs to another page
+    auto adopt = [&](int pg, uint32_t i) {  // this warp's chunk i of the current block belongs to another page than cp
       if (cp >= 0) flush();
+      const uint32_t upto = (2u << i) - 1u;  // bits 0..i (i = 31: wraps to all ones)
+      const uint32_t le = cmask & upto, gt = cmask & ~upto;
       cp = pg;
-      cord = ordinal;
+      cord = ord_base + __popc(le);
       ccount = 0;
-      ps_lo = __ldg(page_start + pg);
-      ps_hi = __ldg(page_start + pg + 1);
+      cp_start_g = le ? g_base + 31 - __clz(le) : last_change_g;
+      cp_end_g = gt ? g_base + __ffs(gt) - 1 : -1;
 #pragma unroll
       for (int g = 0; g < NG; ++g)
 #pragma unroll
@@ -488,23 +528,27 @@ maxsim_rowm_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_c
       const int tt = it.t & 7;
       if (tt == 0) {  // a block of <= 8 tiles = 32 chunks: lane l looks at chunk l
         ord_base += __popc(cmask);
-        pages.begin_block(it, chunk_page, n_units, lane);
+        if (cmask) last_change_g = g_base + 31 - __clz(cmask);
+        g_base += __popc(vmask);
+        pages.take(it, chunk_page, lane);
         int prev = __shfl_up_sync(0xffffffffu, pages.cur, 1);
         if (lane == 0) prev = last_pg;
         const bool valid = pages.cur >= 0;
         vmask = __ballot_sync(0xffffffffu, valid);
         cmask = __ballot_sync(0xffffffffu, valid && pages.cur != prev);
         last_pg = __shfl_sync(0xffffffffu, pages.cur, __popc(vmask) - 1);  // valid chunks are a prefix of the block
+        pages.prefetch(it, chunk_page, n_units, lane);
+        if (cp >= 0 && cp_end_g < 0 && cmask != 0u) cp_end_g = g_base + __ffs(cmask) - 1;  // the first change ends page cp
         if (vmask == 0xffffffffu && (cmask & ~1u) == 0u) {
           // fast path: 8 whole tiles of ONE page (it may begin at this block's first chunk -- 1024-row pages are exactly one
           // block): at most one adoption, then four owned tiles without bookkeeping
-          if (last_pg != cp) adopt(last_pg, ord_base + int(cmask & 1u));
+          if (last_pg != cp) adopt(last_pg, 0u);
           const uint32_t first = seq + ((seq ^ eset) & 1u);
 #pragma unroll
           for (uint32_t k = 0; k < 4; ++k) {
             const uint32_t sq = first + 2u * k;
             const uint32_t buf = sq & (kAcc - 1);
-            mbar_wait(&tfull[buf], (sq / kAcc) & 1);
+            rm_wait(&tfull[buf], (sq / kAcc) & 1);
             tc_fence_after();
 #pragma unroll
             for (int g = 0; g < NG; ++g) {
@@ -530,11 +574,11 @@ maxsim_rowm_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_c
       const uint32_t i = uint32_t(4 * tt + quad);
       const bool mine = (vmask >> i) & 1u;
       const uint32_t buf = seq & (kAcc - 1);
-      mbar_wait(&tfull[buf], (seq / kAcc) & 1);
+      rm_wait(&tfull[buf], (seq / kAcc) & 1);
       tc_fence_after();
       if (mine) {
         const int my_pg = __shfl_sync(0xffffffffu, pages.cur, int(i));
-        if (my_pg != cp) adopt(my_pg, ord_base + __popc(cmask & ((2u << i) - 1u)));
+        if (my_pg != cp) adopt(my_pg, i);
 #pragma unroll
         for (int g = 0; g < NG; ++g) {
           uint32_t v[32];
@@ -549,7 +593,10 @@ maxsim_rowm_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_c
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[buf]);
     }
-    if (cp >= 0) flush();
+    if (cp >= 0) {
+      if (cp_end_g < 0) cp_end_g = g_base + __popc(vmask);  // the page runs to the end of this CTA's stream
+      flush();
+    }
   } else if (KIND == 3 && warp >= 12) {
     // ================================================================ expanders: 2 KB of sign bits -> A tile in TMEM
     // Warp (quad, par): rows quad*32 .. +31 (its TMEM lane quadrant) of the tiles with seq % 2 == par; thread = one row:
@@ -570,7 +617,7 @@ maxsim_rowm_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_c
         }
       }
       const uint32_t stage = seq & uint32_t(kRmARing - 1), phase = (seq / uint32_t(kRmARing)) & 1u;
-      mbar_wait(&rfull[rs], rphase);
+      rm_wait(&rfull[rs], rphase);
       const uint4 bits = ld_shared_v4(raw0 + rs * kRmRawGroupBytes + (seq & 7u) * kRmRawTile);
       __syncwarp();
       if (lane == 0) mbar_arrive(&rempty[rs]);
@@ -580,7 +627,7 @@ maxsim_rowm_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_c
       for (int w = 0; w < 4; ++w)
 #pragma unroll
         for (int m = 0; m < 8; ++m) v[8 * w + m] = (x[w] >> m) & 0x01010101u;
-      mbar_wait(&empty[stage], phase ^ 1);
+      rm_wait(&empty[stage], phase ^ 1);
       tc_fence_after();
       tmem_st_32x32(a_lane + stage * 32u, v);
       tmem_st_wait();
