@@ -281,7 +281,7 @@ maxsim_rowm_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_c
                    const int32_t* __restrict__ chunk_page, const int32_t* __restrict__ unit_start,
                    const int32_t* __restrict__ unit_end, int n_units, const int64_t* __restrict__ page_start,
                    int n_groups_real, const uint32_t* __restrict__ clamp_bits,
-                   typename RmTraits<KIND>::Acc* __restrict__ group_scores, int64_t ld, int num_stages) {
+                   typename RmTraits<KIND>::Acc* __restrict__ group_scores, int64_t ld, int num_stages, int fast_path) {
   using T = RmTraits<KIND>;
   using K = typename T::K;
   using Acc = typename T::Acc;
@@ -539,7 +539,7 @@ maxsim_rowm_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_c
         last_pg = __shfl_sync(0xffffffffu, pages.cur, __popc(vmask) - 1);  // valid chunks are a prefix of the block
         pages.prefetch(it, chunk_page, n_units, lane);
         if (cp >= 0 && cp_end_g < 0 && cmask != 0u) cp_end_g = g_base + __ffs(cmask) - 1;  // the first change ends page cp
-        if (vmask == 0xffffffffu && (cmask & ~1u) == 0u) {
+        if (fast_path && vmask == 0xffffffffu && (cmask & ~1u) == 0u) {
           // fast path: 8 whole tiles of ONE page (it may begin at this block's first chunk -- 1024-row pages are exactly one
           // block): at most one adoption, then four owned tiles without bookkeeping
           if (last_pg != cp) adopt(last_pg, 0u);
@@ -673,7 +673,8 @@ static int launch_rowm_one(b200ms_t* h, const CUtensorMap& tq, const int32_t* to
   kern<<<grid, T::kThreads, smem, s>>>(c.tmap, tq, static_cast<const uint8_t*>(c.rows), c.n_rows, tok_const,
                                       static_cast<const int32_t*>(h->chunk_page.p), us, us + 1, c.n_units,
                                       static_cast<const int64_t*>(h->page_start.p), n_groups_real, clamp_bits,
-                                      static_cast<typename T::Acc*>(scores), ld, stages);
+                                      static_cast<typename T::Acc*>(scores), ld, stages,
+                                      h->rowm_fast_path != 0);
   h->launches++;
   return check_cuda(h, cudaGetLastError(), "launch maxsim_rowm");
 }
