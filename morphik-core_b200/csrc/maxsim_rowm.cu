@@ -23,8 +23,9 @@
 //   > 128 KB in flight per SM), A and B from shared memory.
 // KIND 3 sign bits: rows stay 16 B in HBM.  A bulk-copy ring brings raw bits into shared memory (16 KB slots = 8 tiles, one
 //   request per contiguous run); eight expander warps -- two per TMEM lane quadrant, alternating tiles, one thread per patch row --
-//   turn 16 B of bits into 32 words of {0,1} bytes (shift + mask per word; the K order inside a 32-bit word is permuted,
-//   element 4m+i <- bit m+8i, and the query is expanded with the same permutation, which a dot product cannot see) and store
+//   turn 16 B of bits into 32 words of int8 (ONE AND per word: bit m+8i stays in place as 2^m, the +-1 query carries the
+//   inverse weight 2^(6-m), every product is +-64; the K order inside a 32-bit word is permuted, element 4m+i <- bit m+8i,
+//   and the query is expanded with the same permutation, which a dot product cannot see) and store
 //   them with ONE tcgen05.st straight into TMEM, where tcgen05.mma kind::i8 reads its A operand (no shared-memory store, no
 //   swizzle, no proxy fence).  128 - ham = (128 - popc(q)) + <q', d'> as in maxsim_b1_umma.cu.
 // Two epilogue warps per lane quadrant alternate tiles as well: every per-tile loop in this kernel is a serial chain inside a
@@ -250,11 +251,16 @@ rowm_query_expand_kernel(const uint32_t* __restrict__ q_words /*[rows,4]*/, cons
   if (row >= n_rows) return;
   const bool real = (row & 31) < __ldg(group_ntok + (row >> 5));
   const uint32_t x = __ldg(q_words + idx);
+  // The row expanders leave bit m+8i of a word IN PLACE (byte i of output word m = 2^m * bit for m <= 6, one AND per word;
+  // bit 7 is the int8 sign, so m = 7 is shifted down to 2^6): the query carries the inverse weight W_m = 2^(6-m) (W_7 = 1), every
+  // product is +-64 and the accumulator is 64 * (n11 - n01), exactly.
   uint32_t o[8];
 #pragma unroll
   for (int m = 0; m < 8; ++m) {
     const uint32_t t = (x >> m) & 0x01010101u;                     // element 4m+i <- bit m+8i  (same as the row expanders)
-    o[m] = real ? (t | ((t ^ 0x01010101u) * 0xffu)) : 0u;          // bit 1 -> +1, bit 0 -> -1, padding token -> 0
+    const uint32_t w = m < 7 ? (1u << (6 - m)) : 1u;
+    const uint32_t pos = t * w, neg = (t ^ 0x01010101u) * ((256u - w) & 0xffu);  // bit 1 -> +W, bit 0 -> -W (two's complement byte)
+    o[m] = real ? (pos | neg) : 0u;                                // padding token -> 0
   }
   out[idx * 2] = make_uint4(o[0], o[1], o[2], o[3]);
   out[idx * 2 + 1] = make_uint4(o[4], o[5], o[6], o[7]);
@@ -496,6 +502,7 @@ maxsim_rowm_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_c
           if (g < n_groups_real) {
             Acc v = rm_val(k, Acc(0));
             if (KIND != 3) v = clamp_token_max(clamp_bits, cp, v);
+            if constexpr (KIND == 3) v = v >> 6;  // accumulators are 64 * (n11 - n01): exact
             const Acc sum = warp_sum(Acc(v + Acc(cn[g])));
             if (lane == 0) group_scores[int64_t(g) * ld + cp] = sum;
           }
@@ -624,9 +631,11 @@ maxsim_rowm_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_c
       uint32_t v[32];
       const uint32_t x[4] = {bits.x, bits.y, bits.z, bits.w};
 #pragma unroll
-      for (int w = 0; w < 4; ++w)
+      for (int w = 0; w < 4; ++w) {
 #pragma unroll
-        for (int m = 0; m < 8; ++m) v[8 * w + m] = (x[w] >> m) & 0x01010101u;
+        for (int m = 0; m < 7; ++m) v[8 * w + m] = x[w] & (0x01010101u << m);  // 2^m * bit, in place: one LOP3 per word
+        v[8 * w + 7] = (x[w] >> 1) & 0x40404040u;                                // bit 7 would be the sign: park it at 2^6
+      }
       rm_wait(&empty[stage], phase ^ 1);
       tc_fence_after();
       tmem_st_32x32(a_lane + stage * 32u, v);
