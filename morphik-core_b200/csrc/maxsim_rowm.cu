@@ -44,7 +44,8 @@
 
 namespace bms {
 
-constexpr int kRmSlots = 64;          // page slots of the cross-warp combine table (drift between warps <= 8 tiles = 35 pages)
+constexpr int kRmSlots = 128;         // page slots of the cross-warp combine table: a warp is at most ~2 blocks = 64 pages away from
+                                      // the slowest one (8 accumulators = 8 tiles ahead; a finished page is flushed at the next block)
 constexpr int kRmRawGroups = 6;       // KIND 3: raw-bit ring, slots of 8 tiles = 16 KB (one bulk copy per contiguous run: the copy
 constexpr int kRmGroupTiles = 8;      //   engine keeps only a few requests per SM in flight -- 2 KB requests capped the scan at 1.1 TB/s)
 constexpr uint32_t kRmRawTile = 128 * 16;
@@ -546,6 +547,13 @@ maxsim_rowm_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_c
         last_pg = __shfl_sync(0xffffffffu, pages.cur, __popc(vmask) - 1);  // valid chunks are a prefix of the block
         pages.prefetch(it, chunk_page, n_units, lane);
         if (cp >= 0 && cp_end_g < 0 && cmask != 0u) cp_end_g = g_base + __ffs(cmask) - 1;  // the first change ends page cp
+        if (cp >= 0 && cp_end_g >= 0 && cp_end_g <= g_base) {
+          // page cp ended before this block: hand its maxima over NOW.  Waiting for this warp's next chunk of another page can
+          // take arbitrarily long when its lane quadrant has no rows for a while (runs of units that end in partial tiles), and
+          // the page-slot table is only kRmSlots ordinals deep.
+          flush();
+          cp = -1;
+        }
         if (fast_path && vmask == 0xffffffffu && (cmask & ~1u) == 0u) {
           // fast path: 8 whole tiles of ONE page (it may begin at this block's first chunk -- 1024-row pages are exactly one
           // block): at most one adoption, then four owned tiles without bookkeeping

@@ -213,6 +213,26 @@ def test_rows_as_m_kernel_is_bit_identical_to_query_as_m(dtype, unit_rows_, n_pa
         assert np.array_equal(a.score_matrix(q1), b.score_matrix(q1))
 
 
+@pytest.mark.parametrize("dtype", ["bf16", "binary"])
+def test_rows_as_m_kernel_flushes_finished_pages_early(dtype):
+    """One CTA, 64-row work units: a 128-row page gives lane quadrants 2 and 3 a partial maximum, then 400 pages of <= 64 rows
+    follow whose tiles only fill quadrants 0 and 1 -- those warps must hand the finished page over at the next block, not at
+    their next chunk (which never comes), or the 128-slot page table wraps around under them."""
+    rng = np.random.default_rng(99)
+    lens = [128] + [int(x) for x in rng.integers(33, 65, size=400)] + [128] + [40] * 300
+    pages = make_pages(rng, lens)
+    a = MaxSimIndex(dtype=dtype); a.set_option("rowm", 1)
+    b = MaxSimIndex(dtype=dtype); b.set_option("rowm", 0)
+    if dtype == "binary":
+        b.set_option("b1_tensor", 0)
+    for ix in (a, b):
+        ix.set_tuning(unit_rows=64, max_ctas=1)
+        ix.add_pages(pages)
+    for qs in ([unit_rows(rng, 32)], [unit_rows(rng, 9)]):
+        ga, gb = a.score_matrix(qs), b.score_matrix(qs)
+        assert np.array_equal(ga, gb), (dtype, np.argwhere(ga != gb)[:5])
+
+
 def test_rows_as_m_kernel_binary_matches_oracle_on_uniform_pages():
     """1024-row pages (the BASELINE shape): every page spans 8 tiles and all four epilogue warps; exact integers."""
     rng = np.random.default_rng(77)
