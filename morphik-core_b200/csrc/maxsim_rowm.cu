@@ -46,8 +46,8 @@ namespace bms {
 
 constexpr int kRmSlots = 128;         // page slots of the cross-warp combine table: a warp is at most ~2 blocks = 64 pages away from
                                       // the slowest one (8 accumulators = 8 tiles ahead; a finished page is flushed at the next block)
-constexpr int kRmRawGroups = 6;       // KIND 3: raw-bit ring, slots of 8 tiles = 16 KB (one bulk copy per contiguous run: the copy
-constexpr int kRmGroupTiles = 8;      //   engine keeps only a few requests per SM in flight -- 2 KB requests capped the scan at 1.1 TB/s)
+constexpr int kRmRawGroups = 6;       // KIND 3: raw-bit ring, slots of 8 tiles = 16 KB, one bulk copy per contiguous run (a 2 KB copy
+constexpr int kRmGroupTiles = 8;      //   per tile left the expanders waiting for data although 48 were in flight; measured +4 %)
 constexpr uint32_t kRmRawTile = 128 * 16;
 constexpr uint32_t kRmRawGroupBytes = kRmGroupTiles * kRmRawTile;
 constexpr int kRmMaxStages = 14;      // TMA kinds: 16 / 32 KB patch tiles in flight (HBM latency x bandwidth wants > 128 KB per SM)
@@ -67,7 +67,7 @@ __device__ __forceinline__ void mbar_expect_tx_only(uint64_t* bar, uint32_t byte
 }
 // mbarrier wait with a suspend-time hint: the thread sleeps inside the try_wait until the phase completes (or ~2 us pass) instead of
 // coming back every ~90 cycles.  In this kernel the pollers share their SM sub-partition's issue slots with the warps that
-// work (ncu: 1050 warp instructions per 128-row tile, 18 % of them polling, issue-bound), so fewer polls is throughput.
+// work (ncu: ~1050 warp instructions per 128-row tile, 18 % of them polling); measured neutral on time, fewer wasted slots.
 __device__ __forceinline__ void rm_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
   uint32_t ok;
@@ -81,12 +81,6 @@ __device__ __forceinline__ void rm_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
   } while (!ok);
 }
-__device__ __forceinline__ uint2 ld_shared_v2(uint32_t addr) {
-  uint2 v;
-  asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr) : "memory");
-  return v;
-}
-
 __device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
   uint4 v;
   asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
@@ -286,8 +280,7 @@ __global__ void __launch_bounds__(RmTraits<KIND>::kThreads, 1)
 maxsim_rowm_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constant__ CUtensorMap tmap_q,
                    const uint8_t* __restrict__ raw_rows, int64_t n_rows, const int32_t* __restrict__ tok_const,
                    const int32_t* __restrict__ chunk_page, const int32_t* __restrict__ unit_start,
-                   const int32_t* __restrict__ unit_end, int n_units, const int64_t* __restrict__ page_start,
-                   int n_groups_real, const uint32_t* __restrict__ clamp_bits,
+                   const int32_t* __restrict__ unit_end, int n_units, int n_groups_real, const uint32_t* __restrict__ clamp_bits,
                    typename RmTraits<KIND>::Acc* __restrict__ group_scores, int64_t ld, int num_stages, int fast_path) {
   using T = RmTraits<KIND>;
   using K = typename T::K;
@@ -689,7 +682,7 @@ static int launch_rowm_one(b200ms_t* h, const CUtensorMap& tq, const int32_t* to
   const int32_t* us = static_cast<const int32_t*>(h->unit_start.p);
   kern<<<grid, T::kThreads, smem, s>>>(c.tmap, tq, static_cast<const uint8_t*>(c.rows), c.n_rows, tok_const,
                                       static_cast<const int32_t*>(h->chunk_page.p), us, us + 1, c.n_units,
-                                      static_cast<const int64_t*>(h->page_start.p), n_groups_real, clamp_bits,
+                                      n_groups_real, clamp_bits,
                                       static_cast<typename T::Acc*>(scores), ld, stages,
                                       h->rowm_fast_path != 0);
   h->launches++;
