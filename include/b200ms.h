@@ -283,6 +283,8 @@ int b200ms_set_tuning(b200ms_t* h, int64_t unit_rows, int max_ctas);
  *                     reference, fast_multivector_store.py:553-555); full scans batch pages in page-id order.  0 = clean MaxSim
  *                     (default).  Float and int8 corpora only -- SQL max_sim has no padding.
  *   "zero_copy"       1 (default): host entry points move small calls (<= 256 query rows) through mapped pinned memory
+ *   "host_graph"      1 (default): small unmasked host searches (pack -> score -> top-k) are captured into a CUDA graph on their
+ *                     second use and replayed as one launch; 0 = three plain launches (same results)
  *   "fde_gemm"        1 (default): FDE scan on tcgen05 when fde_dim % 64 == 0, 0 = SIMT scan
  *   "unit_rows", "max_ctas"   work-unit size (needs a new b200ms_set_corpus) and launch width. */
 int b200ms_set_option(b200ms_t* h, const char* name, int64_t value);

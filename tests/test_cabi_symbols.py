@@ -101,3 +101,18 @@ def test_library_matches_sources_and_stale_library_is_detected(tmp_path, monkeyp
     assert bn.stale() and bn.mismatched()
     monkeypatch.setattr(bn, "STAMP", str(tmp_path / "absent"))
     assert bn.stale() and not bn.mismatched()  # no stamp: rebuild wanted, but the library cannot be called wrong
+
+
+def test_every_named_option_is_documented_in_the_header():
+    """b200ms_set_option names (csrc/api.cu) <-> the option list in include/b200ms.h: a knob without documentation is invisible
+    to a ctypes-only host."""
+    import re
+
+    api = open(os.path.join(ROOT, "morphik-core_b200", "csrc", "api.cu")).read()
+    body = api[api.index("B200MS_API int b200ms_set_option"):]
+    body = body[:body.index("\n}\n")]
+    names = set(re.findall(r'n == "([a-z0-9_]+)"', body))
+    assert {"pair_cta", "b1_tensor", "rowm", "zero_pad_compat"} <= names
+    header = open(os.path.join(ROOT, "include", "b200ms.h")).read()
+    missing = sorted(n for n in names if f'"{n}"' not in header)
+    assert not missing, f"options without a line in include/b200ms.h: {missing}"
