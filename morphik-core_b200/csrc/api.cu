@@ -242,7 +242,6 @@ B200MS_API int b200ms_create(int device, b200ms_t** out) {
   if (const char* e = getenv("B200MS_PAIR_CTA")) h->pair_cta = atoi(e);
   if (const char* e = getenv("B200MS_ROWM")) h->rowm = atoi(e) != 0;
   if (const char* e = getenv("B200MS_ROWM_FAST")) h->rowm_fast_path = atoi(e);
-  if (const char* e = getenv("B200MS_ROWM_HINT")) h->rowm_wait_hint = atoi(e);
   if (const char* e = getenv("B200MS_ZERO_COPY")) h->zero_copy = atoi(e);
   if (const char* e = getenv("B200MS_UNIT_ROWS")) { if (atoll(e) > 0) h->unit_rows = atoll(e); }
   if (int e = check_cuda(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking), "cudaStreamCreate")) {

@@ -119,7 +119,6 @@ struct b200ms {
   int tmap_qn_dtype = -1;
   int64_t tmap_qn_rows = -1;
   int tmap_qn_box = 0;
-  int rowm_wait_hint = 1;   // A/B knob (env B200MS_ROWM_HINT): mbarrier try_wait with a suspend-time hint (A/B: neutral to +1 %)
   int rowm_fast_path = 1;   // A/B knob (env B200MS_ROWM_FAST): epilogue fast path for 8-tile blocks inside one page (A/B: faster for every dtype)
   int rowm = 1;  // option "rowm": full scans of <= kRowmMaxGroups query groups run on maxsim_rowm_kernel (0: query-as-M kernels)
   // CUDA graphs of the small zero-copy host search (pack -> score -> top-k): key -> executable graph

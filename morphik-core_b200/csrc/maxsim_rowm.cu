@@ -67,12 +67,9 @@ __device__ __forceinline__ void mbar_expect_tx_only(uint64_t* bar, uint32_t byte
 }
 // mbarrier wait with a suspend-time hint: the thread sleeps inside the try_wait until the phase completes (or ~2 us pass) instead of
 // coming back every ~90 cycles.  In this kernel the pollers share their SM sub-partition's issue slots with the warps that
-// work (ncu: ~1050 warp instructions per 128-row tile, 18 % of them polling); measured neutral on time, fewer wasted slots.
-__device__ __forceinline__ void rm_wait(uint64_t* bar, uint32_t parity, int hint) {
-  if (!hint) {
-    mbar_wait(bar, parity);
-    return;
-  }
+// work (ncu: ~1050 warp instructions per 128-row tile, 18 % of them polling); A/B against plain polling: neutral to +1 %
+// (profiles/r02/rowm_hint_ab.jsonl, measured with a runtime switch that is gone again).
+__device__ __forceinline__ void rm_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
   uint32_t ok;
   do {
@@ -285,7 +282,7 @@ maxsim_rowm_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_c
                    const uint8_t* __restrict__ raw_rows, int64_t n_rows, const int32_t* __restrict__ tok_const,
                    const int32_t* __restrict__ chunk_page, const int32_t* __restrict__ unit_start,
                    const int32_t* __restrict__ unit_end, int n_units, int n_groups_real, const uint32_t* __restrict__ clamp_bits,
-                   typename RmTraits<KIND>::Acc* __restrict__ group_scores, int64_t ld, int num_stages, int fast_path, int wait_hint) {
+                   typename RmTraits<KIND>::Acc* __restrict__ group_scores, int64_t ld, int num_stages, int fast_path) {
   using T = RmTraits<KIND>;
   using K = typename T::K;
   using Acc = typename T::Acc;
@@ -381,7 +378,7 @@ maxsim_rowm_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_c
         };
         for (; it.valid(n_units); it.next(unit_start, unit_end, n_units)) {
           const int64_t row0 = int64_t(it.chunk0()) * kGroup;
-          if (in_group == 0) rm_wait(&rempty[rg], gphase ^ 1, wait_hint);
+          if (in_group == 0) rm_wait(&rempty[rg], gphase ^ 1);
           if (run_tiles > 0 && row0 == run_row0 + int64_t(run_tiles) * 128) {
             ++run_tiles;
           } else {
@@ -408,7 +405,7 @@ maxsim_rowm_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_c
         int stage = 0;
         uint32_t phase = 0;
         for (; it.valid(n_units); it.next(unit_start, unit_end, n_units)) {
-          rm_wait(&empty[stage], phase ^ 1, wait_hint);
+          rm_wait(&empty[stage], phase ^ 1);
           mbar_expect_tx(&full[stage], K::kTileBytes);
           uint8_t* dst = smem_st + size_t(stage) * K::kTileBytes;
           const int row0 = it.chunk0() * kGroup;
@@ -427,15 +424,15 @@ maxsim_rowm_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_c
     constexpr uint32_t idesc = umma_idesc(T::kMmaKind, kTileN, int(kAccCols));
     constexpr uint32_t kTileDesc = K::kTileBytes >> 4;
     if (elect_one()) {  // one thread runs the whole loop: no per-tile elect / warp sync
-      rm_wait(qfull, 0, wait_hint);
+      rm_wait(qfull, 0);
       tc_fence_after();
       const uint64_t a_desc0 = umma_desc_kmajor_sw128(smem_u32(smem_st));
       const uint64_t b_desc0 = umma_desc_kmajor_sw128(smem_u32(smem_q));
       uint32_t stage = 0, phase = 0;
       for (uint32_t seq = 0; seq < total_tiles; ++seq) {
         const uint32_t buf = seq & (kAcc - 1);
-        rm_wait(&full[stage], phase, wait_hint);
-        rm_wait(&tempty[buf], ((seq / kAcc) & 1) ^ 1, wait_hint);
+        rm_wait(&full[stage], phase);
+        rm_wait(&tempty[buf], ((seq / kAcc) & 1) ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + buf * kAccCols;
 #pragma unroll
@@ -560,7 +557,7 @@ maxsim_rowm_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_c
           for (uint32_t k = 0; k < 4; ++k) {
             const uint32_t sq = first + 2u * k;
             const uint32_t buf = sq & (kAcc - 1);
-            rm_wait(&tfull[buf], (sq / kAcc) & 1, wait_hint);
+            rm_wait(&tfull[buf], (sq / kAcc) & 1);
             tc_fence_after();
 #pragma unroll
             for (int g = 0; g < NG; ++g) {
@@ -586,7 +583,7 @@ maxsim_rowm_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_c
       const uint32_t i = uint32_t(4 * tt + quad);
       const bool mine = (vmask >> i) & 1u;
       const uint32_t buf = seq & (kAcc - 1);
-      rm_wait(&tfull[buf], (seq / kAcc) & 1, wait_hint);
+      rm_wait(&tfull[buf], (seq / kAcc) & 1);
       tc_fence_after();
       if (mine) {
         const int my_pg = __shfl_sync(0xffffffffu, pages.cur, int(i));
@@ -629,7 +626,7 @@ maxsim_rowm_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_c
         }
       }
       const uint32_t stage = seq & uint32_t(kRmARing - 1), phase = (seq / uint32_t(kRmARing)) & 1u;
-      rm_wait(&rfull[rs], rphase, wait_hint);
+      rm_wait(&rfull[rs], rphase);
       const uint4 bits = ld_shared_v4(raw0 + rs * kRmRawGroupBytes + (seq & 7u) * kRmRawTile);
       __syncwarp();
       if (lane == 0) mbar_arrive(&rempty[rs]);
@@ -641,7 +638,7 @@ maxsim_rowm_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_c
         for (int m = 0; m < 7; ++m) v[8 * w + m] = x[w] & (0x01010101u << m);  // 2^m * bit, in place: one LOP3 per word
         v[8 * w + 7] = (x[w] >> 1) & 0x40404040u;                                // bit 7 would be the sign: park it at 2^6
       }
-      rm_wait(&empty[stage], phase ^ 1, wait_hint);
+      rm_wait(&empty[stage], phase ^ 1);
       tc_fence_after();
       tmem_st_32x32(a_lane + stage * 32u, v);
       tmem_st_wait();
@@ -688,7 +685,7 @@ static int launch_rowm_one(b200ms_t* h, const CUtensorMap& tq, const int32_t* to
                                       static_cast<const int32_t*>(h->chunk_page.p), us, us + 1, c.n_units,
                                       n_groups_real, clamp_bits,
                                       static_cast<typename T::Acc*>(scores), ld, stages,
-                                      h->rowm_fast_path != 0, h->rowm_wait_hint != 0);
+                                      h->rowm_fast_path != 0);
   h->launches++;
   return check_cuda(h, cudaGetLastError(), "launch maxsim_rowm");
 }
