@@ -140,7 +140,7 @@ class Warp:
             self.done = True
 
 
-def run_model(page_chunks, unit_chunks, seed):
+def run_model(page_chunks, unit_chunks, seed, schedule="random"):
     rng = random.Random(seed)
     tiles, values = build_stream(page_chunks, unit_chunks, rng)
     if not tiles:
@@ -165,7 +165,14 @@ def run_model(page_chunks, unit_chunks, seed):
             return all(x.seq > t_old for x in owners)
         ready = [w for w in warps if may_advance(w)]
         assert ready, "model deadlock"
-        rng.choice(ready).step()
+        if schedule == "run_ahead":    # the fastest warp runs as far ahead as the ring lets it
+            w = max(ready, key=lambda x: (x.seq, rng.random()))
+        elif schedule == "starve":     # one warp only moves when nobody else can
+            others = [x for x in ready if x is not warps[seed % 8]]
+            w = rng.choice(others) if others else ready[0]
+        else:
+            w = rng.choice(ready)
+        w.step()
     assert table.emitted == want
     assert all(c == 0 for c in table.cnt) and all(o is None for o in table.owner)
 
@@ -180,6 +187,16 @@ def test_ragged_pages_and_unit_sizes(seed):
     rng = random.Random(1000 + seed)
     pages = [rng.choice([0, 1, 1, 2, 3, 4, 5, 8, 9, 31, 32, 33, 40]) for _ in range(rng.randrange(1, 600))]
     run_model(pages, rng.choice([2, 4, 13, 32, 128]), seed)
+
+
+@pytest.mark.parametrize("schedule", ["run_ahead", "starve"])
+@pytest.mark.parametrize("seed", range(8))
+def test_adversarial_interleavings_of_one_chunk_pages(seed, schedule):
+    """Worst case for the slot table: every chunk is its own page (32 new pages per block) while one warp lags the full depth of
+    the accumulator ring behind the others."""
+    rng = random.Random(77 + seed)
+    pages = [1] * 700 + [rng.choice([1, 2, 5]) for _ in range(300)]
+    run_model(pages, rng.choice([4, 32, 128]), seed, schedule)
 
 
 @pytest.mark.parametrize("seed", range(4))
