@@ -730,6 +730,7 @@ def run_gpu(args):
            "kernel": "maxsim_rowm_kernel<bf16,NG=1> (patch rows = MMA M operand, query tokens = N)", "achieved": gbs,
            "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
            "peak_kind": f"{peaks['source']} copy bandwidth (read+write; a read-only stream can exceed it)",
+           "frac_of_nominal_7700_gbs": gbs / 7700.0,
            "patch_vectors_per_sec": my_rows / (sm1 * 1e-3), "score_ms": sm1, "step_ms": step1,
            "algorithmic_bytes_per_launch": my_rows * DIM * 2,
            "traffic": (tr["maxsim_rowm<bf16,NG=1>"]["dram_bytes_per_patch_vector"] * my_rows
@@ -795,7 +796,8 @@ def run_gpu(args):
                 g1 = sp * P_PATCH * rb / (s1 * 1e-3) / 1e9
                 ops32 = 2.0 * sp * P_PATCH * DIM * n_q * T_TOK / (s32 * 1e-3) / 1e12
                 pt = {"bytes_per_patch_vector": rb, "one_query": {"score_ms": s1, "achieved": g1, "unit": "GB/s", "peak": peaks["hbm_gbs"],
-                                                                   "frac": g1 / peaks["hbm_gbs"], "bound": "hbm" if name != "binary" else "instruction issue (bit expansion + epilogue), not hbm",
+                                                                   "frac": g1 / peaks["hbm_gbs"], "frac_of_nominal_7700_gbs": g1 / 7700.0,
+                                                                   "bound": "hbm" if name != "binary" else "instruction issue (bit expansion + epilogue), not hbm",
                                                                    "kernel": "maxsim_rowm_kernel",
                                                                    "patch_vectors_per_sec": sp * P_PATCH / (s1 * 1e-3)},
                       "batch32": {"score_ms": s32, "achieved": ops32, "unit": "TFLOP/s" if name in ("bf16", "fp8") else "TOP/s",
